@@ -1,0 +1,121 @@
+// common.cuh -- shared device helpers for libdadmm_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <atomic>
+#include <cstdio>
+
+namespace dadmm {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+#define DADMM_FAIL(code, ...)                                   \
+    do {                                                        \
+        snprintf(::dadmm::g_err, sizeof(::dadmm::g_err), __VA_ARGS__); \
+        return (code);                                          \
+    } while (0)
+
+#define DADMM_CUDA(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            snprintf(::dadmm::g_err, sizeof(::dadmm::g_err), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, \
+                     cudaGetErrorString(_e));                                                  \
+            return (int)_e;                                                                    \
+        }                                                                                      \
+    } while (0)
+
+#define DADMM_LAUNCHED()                         \
+    do {                                         \
+        ::dadmm::g_launches.fetch_add(1);        \
+        DADMM_CUDA(cudaGetLastError());          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic that mirrors the reference's eager PyTorch ops: one IEEE rounding per op, never
+// contracted into an FMA (unfolded_DLASSO.py:73-99 evaluates `a*b` and `+` as separate kernels).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
+// torch.clamp(x, -c, c): NaN propagates (both comparisons false).
+template <typename T>
+__device__ __forceinline__ T clamp_sym(T x, T c) {
+    return x < -c ? -c : (x > c ? c : x);
+}
+// torch.clamp backward mask: closed interval, false for NaN.
+template <typename T>
+__device__ __forceinline__ bool in_closed(T x, T c) {
+    return (x >= -c) && (x <= c);
+}
+// torch.sign: 0 for 0 and for NaN.
+template <typename T>
+__device__ __forceinline__ T sign_of(T x) {
+    return (T)((x > (T)0) - (x < (T)0));
+}
+template <typename T>
+__device__ __forceinline__ bool finite_val(T x) {
+    return isfinite(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small aligned vectors for 4/8/16-byte global and shared accesses.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int N>
+struct alignas(sizeof(T) * N) Vec {
+    T v[N];
+};
+
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> ld_vec(const T* p) {
+    return *reinterpret_cast<const Vec<T, N>*>(p);
+}
+// streaming (read-once) global load: bypass L1 allocation
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> ld_stream(const T* p) {
+    Vec<T, N> r;
+    if constexpr (sizeof(T) * N == 16) {
+        int4 t = __ldcs(reinterpret_cast<const int4*>(p));
+        r = *reinterpret_cast<Vec<T, N>*>(&t);
+    } else if constexpr (sizeof(T) * N == 8) {
+        int2 t = __ldcs(reinterpret_cast<const int2*>(p));
+        r = *reinterpret_cast<Vec<T, N>*>(&t);
+    } else {
+        static_assert(sizeof(T) * N == 4, "unsupported vector width");
+        int t = __ldcs(reinterpret_cast<const int*>(p));
+        r = *reinterpret_cast<Vec<T, N>*>(&t);
+    }
+    return r;
+}
+template <typename T, int N>
+__device__ __forceinline__ void st_vec(T* p, const Vec<T, N>& x) {
+    *reinterpret_cast<Vec<T, N>*>(p) = x;
+}
+template <typename T, int N>
+__device__ __forceinline__ void st_stream(T* p, const Vec<T, N>& x) {
+    if constexpr (sizeof(T) * N == 16) {
+        __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(&x));
+    } else if constexpr (sizeof(T) * N == 8) {
+        __stcs(reinterpret_cast<int2*>(p), *reinterpret_cast<const int2*>(&x));
+    } else {
+        __stcs(reinterpret_cast<int*>(p), *reinterpret_cast<const int*>(&x));
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div64(long long a, long long b) { return (a + b - 1) / b; }
+
+}  // namespace dadmm

@@ -1,0 +1,431 @@
+// dadmm_abi.cu -- extern "C" entry points of libdadmm_sm100.so (see include/dadmm.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/dadmm.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+#include "contract_simt.cuh"
+#include "contract_tc.cuh"
+#include "step.cuh"
+
+namespace dadmm {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------------------------------
+// tile configuration of the step kernels
+// ------------------------------------------------------------------------------------------
+struct StepCfg {
+    int vec, TB, nchunks, grid;
+    size_t smem_fwd, smem_bwd;
+};
+
+static bool aligned_to(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// narr_fwd: shared-memory tile arrays the forward needs (0..2); the backward always needs 2 (+R scalars)
+static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, StepCfg* c) {
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    const size_t budget = 100 * 1024;  // two CTAs per SM
+    int TB = std::max(1, std::min(B, (16 + P - 1) / P));
+    for (int vec = max_vec; vec >= 1; vec >>= 1) {
+        if (n % vec) continue;
+        for (int tb = TB; tb >= 1; --tb) {
+            const size_t R = (size_t)tb * P, CH = 32 * vec;
+            const size_t sf = (size_t)narr_fwd * R * CH * es;
+            const size_t sb = 2 * R * CH * es + R * es;
+            if (std::max(sf, sb) <= budget || (vec == 1 && tb == 1 && std::max(sf, sb) <= 227 * 1024)) {
+                c->vec = vec;
+                c->TB = tb;
+                c->nchunks = (n + (int)CH - 1) / (int)CH;
+                c->grid = c->nchunks * ((B + tb - 1) / tb);
+                c->smem_fwd = sf;
+                c->smem_bwd = sb;
+                return 0;
+            }
+        }
+    }
+    DADMM_FAIL(-2, "step kernels: P=%d does not fit in shared memory", P);
+}
+
+// Vector width of the step kernels: the widest of {4,2,1} (fp32) / {2,1} (fp64) that divides n.  It
+// depends on n only, so that dadmm_reduce_hyp can recompute the chunking; every tensor pointer must
+// then be aligned to vec*sizeof(T) (torch allocations and [k] slices of [K,B,P,n] tensors are).
+static int max_vec_for(int dtype, int n) {
+    int vec = dtype == DADMM_F64 ? 2 : 4;
+    while (vec > 1 && (n % vec)) vec >>= 1;
+    return vec;
+}
+static int check_aligned(int dtype, int vec, std::initializer_list<const void*> ptrs) {
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    for (const void* p : ptrs)
+        if (!aligned_to(p, es * vec)) DADMM_FAIL(-5, "step kernels: tensor pointer %p is not %zu-byte aligned", p, es * vec);
+    return 0;
+}
+
+template <typename K>
+static int allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) DADMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static int check_graph(const dadmm_graph* g, int P) {
+    if (!g || !g->ev_ptr || !g->ev_idx || !g->deg) DADMM_FAIL(-3, "graph: null CSR pointers");
+    if (g->P != P) DADMM_FAIL(-3, "graph: P mismatch (%d vs %d)", g->P, P);
+    if (g->n_graphs < 1) DADMM_FAIL(-3, "graph: n_graphs < 1");
+    return 0;
+}
+
+template <typename T, int VEC>
+static int launch_step_fwd_t(const StepFwdParams<T>& p, const StepCfg& c, cudaStream_t s) {
+    if (int e = allow_smem(step_fwd_kernel<T, VEC>, c.smem_fwd)) return e;
+    step_fwd_kernel<T, VEC><<<c.grid, kStepThreads, c.smem_fwd, s>>>(p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+template <typename T, int VEC>
+static int launch_step_bwd_t(const StepBwdParams<T>& p, const StepCfg& c, cudaStream_t s) {
+    if (int e = allow_smem(step_bwd_kernel<T, VEC>, c.smem_bwd)) return e;
+    step_bwd_kernel<T, VEC><<<c.grid, kStepThreads, c.smem_bwd, s>>>(p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+template <typename T>
+static int step_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl,
+                         const dadmm_hyp* h, const void* y, const void* U, const void* delta, const void* a,
+                         const void* atb, void* y_next, void* U_next, void* delta_next, void* graw, int32_t* flags,
+                         cudaStream_t s) {
+    StepFwdParams<T> p;
+    p.B = B; p.P = P; p.n = n;
+    p.ev_ptr = g->ev_ptr; p.ev_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
+    p.hyp = (const T*)h->ptr; p.hsb = h->stride_b; p.hsp = h->stride_p; p.hsc = h->stride_c;
+    p.G = (T)cl->G; p.V = (T)cl->V; p.Uc = (T)cl->Uc;
+    p.hasD = std::isfinite(cl->D) ? 1 : 0;
+    p.D = p.hasD ? (T)cl->D : std::numeric_limits<T>::infinity();
+    p.y = (const T*)y; p.U = (const T*)U; p.delta = (const T*)delta; p.a = (const T*)a; p.atb = (const T*)atb;
+    p.y_next = (T*)y_next; p.U_next = (T*)U_next; p.delta_next = (T*)delta_next; p.graw = (T*)graw;
+    p.flags = flags;
+    const int narr = (delta ? 0 : 1) + ((U_next || delta_next) ? 1 : 0);
+    StepCfg c;
+    if (int e = step_cfg(dtype, B, P, n, narr, max_vec_for(dtype, n), &c)) return e;
+    if (int e = check_aligned(dtype, c.vec, {y, U, delta, a, atb, y_next, U_next, delta_next, graw})) return e;
+    p.TB = c.TB;
+    if constexpr (sizeof(T) == 4) {
+        if (c.vec == 4) return launch_step_fwd_t<T, 4>(p, c, s);
+    }
+    if (c.vec == 2) return launch_step_fwd_t<T, 2>(p, c, s);
+    return launch_step_fwd_t<T, 1>(p, c, s);
+}
+
+template <typename T>
+static int step_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl,
+                         const dadmm_hyp* h, const void* y, const void* U, const void* delta, const void* graw,
+                         const void* y_next, const void* gy_a, const void* gy_b, const void* gU_next,
+                         const void* gd_next, const void* label, double loss_coef, void* gy, void* ga, void* gU,
+                         void* gd, void* partials, cudaStream_t s) {
+    StepBwdParams<T> p;
+    p.B = B; p.P = P; p.n = n;
+    p.ev_ptr = g->ev_ptr; p.ev_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
+    p.hyp = (const T*)h->ptr; p.hsb = h->stride_b; p.hsp = h->stride_p; p.hsc = h->stride_c;
+    p.G = (T)cl->G; p.V = (T)cl->V; p.Uc = (T)cl->Uc;
+    p.hasD = std::isfinite(cl->D) ? 1 : 0;
+    p.D = p.hasD ? (T)cl->D : std::numeric_limits<T>::infinity();
+    p.y = (const T*)y; p.U = (const T*)U; p.delta = (const T*)delta; p.graw = (const T*)graw;
+    p.y_next = (const T*)y_next;
+    p.gy_a = (const T*)gy_a; p.gy_b = (const T*)gy_b; p.gU_next = (const T*)gU_next; p.gd_next = (const T*)gd_next;
+    p.label = (loss_coef != 0.0) ? (const T*)label : nullptr;
+    p.loss_coef = (T)loss_coef;
+    p.gy = (T*)gy; p.ga = (T*)ga; p.gU = (T*)gU; p.gd = (T*)gd; p.partials = (T*)partials;
+    StepCfg c;
+    if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return e;
+    if (int e = check_aligned(dtype, c.vec, {y, U, delta, graw, y_next, gy_a, gy_b, gU_next, gd_next, label, gy, ga, gU, gd}))
+        return e;
+    p.TB = c.TB;
+    if constexpr (sizeof(T) == 4) {
+        if (c.vec == 4) return launch_step_bwd_t<T, 4>(p, c, s);
+    }
+    if (c.vec == 2) return launch_step_bwd_t<T, 2>(p, c, s);
+    return launch_step_bwd_t<T, 1>(p, c, s);
+}
+
+// The partial-sum buffer is laid out for the coarsest chunking the backward may pick (vec=1).
+static size_t partials_elems(int B, int P, int n) { return (size_t)((n + 31) / 32) * B * P * 4; }
+
+template <typename T>
+static int reduce_hyp_impl(int dtype, int B, int P, int n, const void* partials, int per_sample, void* ghyp,
+                           int64_t sb, int64_t sp, int64_t sc, int accumulate, int nchunks, cudaStream_t s) {
+    if (per_sample) {
+        const long long tot = (long long)B * P;
+        reduce_hyp_sample_kernel<T><<<(unsigned)ceil_div64(tot, 256), 256, 0, s>>>((const T*)partials, nchunks, B, P,
+                                                                                   (T*)ghyp, sb, sp, sc, accumulate);
+    } else {
+        reduce_hyp_table_kernel<T><<<P, 256, 0, s>>>((const T*)partials, nchunks, B, P, (T*)ghyp, sp, sc, accumulate);
+    }
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+// chunk count the backward kernel uses for (dtype, B, P, n) -- same derivation as step_bwd_impl
+static int bwd_nchunks(int dtype, int B, int P, int n, int* out) {
+    StepCfg c;
+    if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return e;
+    *out = c.nchunks;
+    return 0;
+}
+
+static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in, const void* W, int64_t w_sp,
+                         int64_t w_si, int64_t w_sk, const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk,
+                         void* out, int64_t o_sb, int64_t o_sp, int64_t o_si, int accumulate, void* ws,
+                         size_t ws_bytes, cudaStream_t s) {
+    if (B <= 0 || P <= 0 || n_out <= 0 || n_in <= 0) DADMM_FAIL(-1, "contract: bad dims");
+    if (!W || !x || !out) DADMM_FAIL(-1, "contract: null pointer");
+    if (dtype == DADMM_F32) {
+        const bool tc_ok = tc::shape_supported(B, P, n_out, n_in, W, w_sp, w_si, w_sk, x, x_sb, x_sp, x_sk, out, o_sb,
+                                               o_sp, o_si);
+        if (algo == DADMM_ALGO_TC_3XTF32 && !tc_ok) DADMM_FAIL(-4, "contract: shape/layout not supported by the tcgen05 kernel");
+        if (tc_ok && (algo == DADMM_ALGO_TC_3XTF32 || algo == DADMM_ALGO_AUTO))
+            return tc::launch(B, P, n_out, n_in, (const float*)W, (const float*)x, (float*)out, x_sb, o_sb, accumulate, ws,
+                              ws_bytes, s);
+        GemmParams<float> p{B, P, n_out, n_in, (const float*)W, w_sp, w_si, w_sk, (const float*)x, x_sb, x_sp, x_sk,
+                            (float*)out, o_sb, o_sp, o_si, accumulate};
+        return launch_contract_simt<float>(p, s);
+    } else if (dtype == DADMM_F64) {
+        if (algo == DADMM_ALGO_TC_3XTF32) DADMM_FAIL(-4, "contract: tcgen05 path is fp32 only");
+        GemmParams<double> p{B, P, n_out, n_in, (const double*)W, w_sp, w_si, w_sk, (const double*)x, x_sb, x_sp, x_sk,
+                             (double*)out, o_sb, o_sp, o_si, accumulate};
+        return launch_contract_simt<double>(p, s);
+    }
+    DADMM_FAIL(-1, "contract: unknown dtype %d", dtype);
+}
+
+}  // namespace dadmm
+
+using namespace dadmm;
+
+extern "C" {
+
+int dadmm_abi_version(void) { return DADMM_ABI_VERSION; }
+const char* dadmm_last_error(void) { return g_err; }
+int64_t dadmm_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dadmm_device_check(void) {
+    int dev = 0, major = 0, minor = 0;
+    DADMM_CUDA(cudaGetDevice(&dev));
+    DADMM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    DADMM_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) DADMM_FAIL(-10, "libdadmm_sm100 needs an sm_100 device, found sm_%d%d", major, minor);
+    return 0;
+}
+
+int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in, const void* W, int64_t w_sp, int64_t w_si,
+                   int64_t w_sk, const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk, void* out, int64_t o_sb,
+                   int64_t o_sp, int64_t o_si, int accumulate, void* ws, size_t ws_bytes, dadmm_stream_t stream) {
+    return contract_impl(dtype, algo, B, P, n_out, n_in, W, w_sp, w_si, w_sk, x, x_sb, x_sp, x_sk, out, o_sb, o_sp, o_si,
+                         accumulate, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in) {
+    if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return 0;
+    return tc::workspace_bytes(B, P, n_out, n_in);
+}
+
+int dadmm_contract_uses_tensor_cores(int dtype, int algo, int B, int P, int n_out, int n_in) {
+    if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return 0;
+    return tc::dims_supported(B, P, n_out, n_in) ? 1 : 0;
+}
+
+int dadmm_step_fwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,
+                   const dadmm_hyp* hyp, const void* y, const void* U, const void* delta, const void* AtAy,
+                   const void* Atb, void* y_next, void* U_next, void* delta_next, void* grad_raw, int32_t* flags,
+                   dadmm_stream_t stream) {
+    if (B <= 0 || P <= 0 || n <= 0) DADMM_FAIL(-1, "step_fwd: bad dims");
+    if (!clamps || !hyp || !hyp->ptr || !y || !U || !AtAy || !Atb || !y_next) DADMM_FAIL(-1, "step_fwd: null pointer");
+    if (int e = check_graph(graph, P)) return e;
+    if (dtype == DADMM_F32)
+        return step_fwd_impl<float>(dtype, B, P, n, graph, clamps, hyp, y, U, delta, AtAy, Atb, y_next, U_next, delta_next,
+                                    grad_raw, flags, (cudaStream_t)stream);
+    if (dtype == DADMM_F64)
+        return step_fwd_impl<double>(dtype, B, P, n, graph, clamps, hyp, y, U, delta, AtAy, Atb, y_next, U_next, delta_next,
+                                     grad_raw, flags, (cudaStream_t)stream);
+    DADMM_FAIL(-1, "step_fwd: unknown dtype %d", dtype);
+}
+
+int dadmm_step_bwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,
+                   const dadmm_hyp* hyp, const void* y, const void* U, const void* delta, const void* grad_raw,
+                   const void* y_next, const void* gy_next_a, const void* gy_next_b, const void* gU_next,
+                   const void* gdelta_next, const void* label, double loss_coef, void* gy, void* gAtAy, void* gU,
+                   void* gdelta, void* ghyp_partials, dadmm_stream_t stream) {
+    if (B <= 0 || P <= 0 || n <= 0) DADMM_FAIL(-1, "step_bwd: bad dims");
+    if (!clamps || !hyp || !hyp->ptr || !y || !U || !grad_raw || !y_next || !gy || !gAtAy || !gU || !ghyp_partials)
+        DADMM_FAIL(-1, "step_bwd: null pointer");
+    if (int e = check_graph(graph, P)) return e;
+    if (dtype == DADMM_F32)
+        return step_bwd_impl<float>(dtype, B, P, n, graph, clamps, hyp, y, U, delta, grad_raw, y_next, gy_next_a, gy_next_b,
+                                    gU_next, gdelta_next, label, loss_coef, gy, gAtAy, gU, gdelta, ghyp_partials,
+                                    (cudaStream_t)stream);
+    if (dtype == DADMM_F64)
+        return step_bwd_impl<double>(dtype, B, P, n, graph, clamps, hyp, y, U, delta, grad_raw, y_next, gy_next_a, gy_next_b,
+                                     gU_next, gdelta_next, label, loss_coef, gy, gAtAy, gU, gdelta, ghyp_partials,
+                                     (cudaStream_t)stream);
+    DADMM_FAIL(-1, "step_bwd: unknown dtype %d", dtype);
+}
+
+size_t dadmm_partials_elems(int dtype, int B, int P, int n) {
+    (void)dtype;
+    return partials_elems(B, P, n);
+}
+
+int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, int per_sample, void* ghyp,
+                     int64_t stride_b, int64_t stride_p, int64_t stride_c, int accumulate, dadmm_stream_t stream) {
+    if (!ghyp_partials || !ghyp) DADMM_FAIL(-1, "reduce_hyp: null pointer");
+    int nchunks = 0;
+    if (int e = bwd_nchunks(dtype, B, P, n, &nchunks)) return e;
+    if (dtype == DADMM_F32)
+        return reduce_hyp_impl<float>(dtype, B, P, n, ghyp_partials, per_sample, ghyp, stride_b, stride_p, stride_c,
+                                      accumulate, nchunks, (cudaStream_t)stream);
+    if (dtype == DADMM_F64)
+        return reduce_hyp_impl<double>(dtype, B, P, n, ghyp_partials, per_sample, ghyp, stride_b, stride_p, stride_c,
+                                       accumulate, nchunks, (cudaStream_t)stream);
+    DADMM_FAIL(-1, "reduce_hyp: unknown dtype %d", dtype);
+}
+
+size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward) {
+    (void)K;
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    const size_t N = (size_t)B * P * n;
+    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    if (!backward) return cw + 3 * N * es;                                // AtAy + two U ping-pong buffers
+    return cw + 4 * N * es + (partials_elems(B, P, n) * es + 255) / 256 * 256;  // gy, ga, gU, gd + partials
+}
+
+int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                       const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb, const void* y0,
+                       const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
+                       int32_t* flags, dadmm_stream_t stream) {
+    if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_fwd: bad dims");
+    if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
+    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0)) DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
+    if (int e = check_graph(graph, P)) return e;
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    const size_t N = (size_t)B * P * n, NB = N * es;
+    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    char* w8 = (char*)ws;
+    void* cws = w8;
+    char* a = w8 + cw;
+    char* pp[2] = {a + NB, a + 2 * NB};
+    const int64_t sn = n, sPn = (int64_t)P * n;
+    for (int k = 0; k < K; ++k) {
+        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
+        const char* Uk = k ? (U_save ? (const char*)U_save + (size_t)(k - 1) * NB : pp[(k - 1) & 1]) : (const char*)U0;
+        char* Un = (k == K - 1) ? nullptr : (U_save ? (char*)U_save + (size_t)k * NB : pp[k & 1]);
+        if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, cws,
+                                  cw, (cudaStream_t)stream))
+            return e;
+        dadmm_hyp h{(const char*)hyp + (size_t)k * P * 4 * es, 0, 4, 1};
+        if (int e = dadmm_step_fwd(dtype, B, P, n, graph, clamps + k, &h, yk, Uk, k ? nullptr : d0, a, Atb,
+                                   (char*)Y + (size_t)k * NB, Un, nullptr, R_save ? (char*)R_save + (size_t)k * NB : nullptr,
+                                   flags ? flags + k : nullptr, stream))
+            return e;
+    }
+    return 0;
+}
+
+int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                       const dadmm_clamps* clamps, const void* hyp, const void* Wt, const void* y0, const void* U0,
+                       const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
+                       const void* label, const double* loss_coef, void* ghyp, void* ws, size_t ws_bytes,
+                       dadmm_stream_t stream) {
+    if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_bwd: bad dims");
+    if (!clamps || !hyp || !Wt || !y0 || !U0 || !d0 || !Y || !R_save || !ghyp || !ws) DADMM_FAIL(-1, "unfolded_bwd: null pointer");
+    if (K > 1 && !U_save) DADMM_FAIL(-1, "unfolded_bwd: U_save required");
+    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 1)) DADMM_FAIL(-1, "unfolded_bwd: workspace too small");
+    if (int e = check_graph(graph, P)) return e;
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    const size_t N = (size_t)B * P * n, NB = N * es;
+    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    char* w8 = (char*)ws;
+    void* cws = w8;
+    char *gy = w8 + cw, *ga = gy + NB, *gU = ga + NB, *gd = gU + NB, *part = gd + NB;
+    const int64_t sn = n, sPn = (int64_t)P * n;
+    for (int k = K - 1; k >= 0; --k) {
+        const bool first = (k == K - 1);
+        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
+        const char* Uk = k ? (const char*)U_save + (size_t)(k - 1) * NB : (const char*)U0;
+        dadmm_hyp h{(const char*)hyp + (size_t)k * P * 4 * es, 0, 4, 1};
+        const double coef = (label && loss_coef) ? loss_coef[k] : 0.0;
+        if (int e = dadmm_step_bwd(dtype, B, P, n, graph, clamps + k, &h, yk, Uk, k ? nullptr : d0,
+                                   (const char*)R_save + (size_t)k * NB, (const char*)Y + (size_t)k * NB,
+                                   first ? nullptr : gy, gY ? (const char*)gY + (size_t)k * NB : nullptr,
+                                   first ? nullptr : gU, first ? nullptr : gd, label, coef, gy, ga, gU, gd, part, stream))
+            return e;
+        if (int e = dadmm_reduce_hyp(dtype, B, P, n, part, 0, (char*)ghyp + (size_t)k * P * 4 * es, 0, 4, 1, 0, stream))
+            return e;
+        if (k > 0) {
+            if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, gy, sPn, sn, 1, 1,
+                                      cws, cw, (cudaStream_t)stream))
+                return e;
+        }
+    }
+    return 0;
+}
+
+size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n) {
+    (void)dtype; (void)B; (void)P; (void)n;
+    return (size_t)K * 1024 * sizeof(double);
+}
+
+int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const void* Y, const void* label, void* losses,
+                   void* ws, size_t ws_bytes, dadmm_stream_t stream) {
+    if (K <= 0 || B <= 0 || P <= 0 || n <= 0 || B_norm <= 0) DADMM_FAIL(-1, "loss_fwd: bad dims");
+    if (!Y || !label || !losses || !ws) DADMM_FAIL(-1, "loss_fwd: null pointer");
+    if (ws_bytes < dadmm_loss_ws_bytes(dtype, K, B, P, n)) DADMM_FAIL(-1, "loss_fwd: workspace too small");
+    const long long per_k = (long long)B * P * n;
+    const int nblk = (int)std::min<long long>(1024, ceil_div64(per_k, 256 * 4));
+    const double inv = 1.0 / ((double)P * (double)B_norm * (double)n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == DADMM_F32) {
+        loss_partial_kernel<float><<<dim3(nblk, K), 256, 0, s>>>((const float*)Y, (const float*)label, B, P, n, (double*)ws);
+        DADMM_LAUNCHED();
+        loss_final_kernel<float><<<K, 256, 0, s>>>((const double*)ws, nblk, K, inv, (float*)losses);
+        DADMM_LAUNCHED();
+    } else if (dtype == DADMM_F64) {
+        loss_partial_kernel<double><<<dim3(nblk, K), 256, 0, s>>>((const double*)Y, (const double*)label, B, P, n, (double*)ws);
+        DADMM_LAUNCHED();
+        loss_final_kernel<double><<<K, 256, 0, s>>>((const double*)ws, nblk, K, inv, (double*)losses);
+        DADMM_LAUNCHED();
+    } else {
+        DADMM_FAIL(-1, "loss_fwd: unknown dtype %d", dtype);
+    }
+    return 0;
+}
+
+int dadmm_loss_bwd(int dtype, int K, int B, int P, int n, const void* Y, const void* label, const double* coef, void* gY,
+                   dadmm_stream_t stream) {
+    if (K <= 0 || B <= 0 || P <= 0 || n <= 0) DADMM_FAIL(-1, "loss_bwd: bad dims");
+    if (!Y || !label || !coef || !gY) DADMM_FAIL(-1, "loss_bwd: null pointer");
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    const long long per_k = (long long)B * P * n;
+    const int nblk = (int)std::min<long long>(148 * 16, ceil_div64(per_k, 256));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int k = 0; k < K; ++k) {
+        char* g = (char*)gY + (size_t)k * per_k * es;
+        const char* y = (const char*)Y + (size_t)k * per_k * es;
+        if (coef[k] == 0.0) {
+            DADMM_CUDA(cudaMemsetAsync(g, 0, (size_t)per_k * es, s));
+        } else if (dtype == DADMM_F32) {
+            loss_bwd_kernel<float><<<nblk, 256, 0, s>>>((const float*)y, (const float*)label, B, P, n, (float)coef[k], (float*)g);
+            DADMM_LAUNCHED();
+        } else if (dtype == DADMM_F64) {
+            loss_bwd_kernel<double><<<nblk, 256, 0, s>>>((const double*)y, (const double*)label, B, P, n, coef[k], (double*)g);
+            DADMM_LAUNCHED();
+        } else {
+            DADMM_FAIL(-1, "loss_bwd: unknown dtype %d", dtype);
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+"""Host-side wrappers of the C ABI (``include/dadmm.h``) and the ``torch.autograd.Function``s built
+on them.  PyTorch supplies device memory, streams and autograd plumbing only; every arithmetic
+operation of the hot path runs in ``libdadmm_sm100.so``.
+
+Reference lines replaced (paths relative to the reference checkout):
+  contract / Contract         unfolded_DLASSO.py:69-71, :120-124  (+ autograd MmBackward)
+  step_fwd / step_bwd / Step  unfolded_DLASSO.py:73-99, :127-140; gnn_dlasso_models_progressive.py:205-232
+  Unfolded                    unfolded_DLASSO.py:53-109 and loss.backward() through it
+  MSELoss                     gnn_dlasso_utils.py:27-88
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, dtype_code, require_cuda, device_guard
+from .graph import BatchGraph
+
+INF = float("inf")
+
+
+# ---------------------------------------------------------------------------------------------
+# clamp schedules
+# ---------------------------------------------------------------------------------------------
+def clamps_model1(k: int) -> Tuple[float, float, float, float]:
+    """(G, V, D, Uc) of iteration k: unfolded_DLASSO.py:80 ``max(1,30-k)``, :92 ``max(10,200-3k)``."""
+    v = max(10.0, 200.0 - k * 3)
+    return (max(1.0, 30.0 - k), v, INF, v)
+
+
+def clamps_model3(k: int = 0) -> Tuple[float, float, float, float]:
+    """gnn_dlasso_models_progressive.py:212,224,229,232: fixed 10 / 100 / 20 / 100."""
+    return (10.0, 100.0, 20.0, 100.0)
+
+
+def _clamps_array(clamps: Sequence[Tuple[float, float, float, float]]):
+    arr = (_lib.Clamps * len(clamps))()
+    for i, (g, v, d, u) in enumerate(clamps):
+        arr[i] = _lib.Clamps(g, v, d, u)
+    return arr
+
+
+def _algo(algo) -> int:
+    return _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
+
+
+def _state3(t: torch.Tensor) -> torch.Tensor:
+    """[B,P,n,1] or [B,P,n] -> contiguous [B,P,n] view/copy."""
+    if t.dim() == 4:
+        t = t.squeeze(-1)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# raw ops
+# ---------------------------------------------------------------------------------------------
+def contract(W: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+             algo="auto") -> torch.Tensor:
+    """out[b,p,:] (+)= W[p] @ x[b,p,:].  W [P,n_out,n_in], x [B,P,n_in] -> out [B,P,n_out]."""
+    dev = require_cuda(W, x, out)
+    W, x = W.contiguous(), x.contiguous()
+    P, n_out, n_in = W.shape
+    B = x.shape[0]
+    assert x.shape == (B, P, n_in), (x.shape, W.shape)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((B, P, n_out), dtype=x.dtype, device=dev)
+    assert out.is_contiguous() and out.shape == (B, P, n_out) and out.dtype == x.dtype == W.dtype
+    dt, al = dtype_code(x), _algo(algo)
+    with device_guard(dev):
+        wsb = lib.dadmm_contract_ws_bytes(dt, al, B, P, n_out, n_in)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+        check(lib.dadmm_contract(dt, al, B, P, n_out, n_in, ptr(W), n_out * n_in, n_in, 1, ptr(x), P * n_in, n_in, 1,
+                                 ptr(out), P * n_out, n_out, 1, int(accumulate), ptr(ws), wsb, stream_ptr(dev)),
+              "dadmm_contract")
+    return out
+
+
+def atx(A: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``compute_Atx`` (unfolded_DLASSO.py:120-124): Atx[:,p] = A[0,p].T @ x[:,p].
+    A [1,P,m,n]; x [Bx,P,m,c] -> [Bx,P,n,c]."""
+    dev = require_cuda(A, x)
+    A, x = A.contiguous(), x.contiguous()
+    _, P, m, n = A.shape
+    Bx, c = x.shape[0], x.shape[3]
+    assert x.shape[1] == P and x.shape[2] == m
+    out = torch.empty((Bx, P, n, c), dtype=x.dtype, device=dev)
+    dt = dtype_code(x)
+    with device_guard(dev):
+        for bx in range(Bx if c > 1 else 1):
+            # "rows" of the contraction are the c columns of one batch entry (c>1), or the batch (c==1)
+            xb, ob = (x[bx], out[bx]) if c > 1 else (x, out)
+            rows = c if c > 1 else Bx
+            x_sb, x_sk = (1, c) if c > 1 else (P * m, 1)
+            o_sb, o_si = (1, c) if c > 1 else (P * n, 1)
+            check(lib.dadmm_contract(dt, _lib.ALGO_SIMT, rows, P, n, m, ptr(A), m * n, 1, n, ptr(xb), x_sb, m * c, x_sk,
+                                     ptr(ob), o_sb, n * c, o_si, 0, None, 0, stream_ptr(dev)), "dadmm_contract(Atx)")
+    return out
+
+
+def _hyp_struct(hyp: torch.Tensor, B: int, P: int) -> _lib.Hyp:
+    """hyp [P,4] (shared, model #1 row) or [B,4,P] (per sample, model #3 layout)."""
+    if hyp.dim() == 2:
+        assert hyp.shape == (P, 4) and hyp.is_contiguous()
+        return _lib.Hyp(hyp.data_ptr(), 0, 4, 1)
+    assert hyp.shape == (B, 4, P) and hyp.is_contiguous(), hyp.shape
+    return _lib.Hyp(hyp.data_ptr(), 4 * P, 1, P)
+
+
+def step_fwd(graph: BatchGraph, clamps, hyp, y, U, delta, AtAy, Atb, want_delta=True, want_U=True, want_graw=True,
+             flags: Optional[torch.Tensor] = None):
+    """One D-ADMM iteration on [B,P,n] tensors; ``delta=None`` recomputes clampD(2L y).
+    Returns (y_next, U_next|None, delta_next|None, grad_raw|None)."""
+    dev = require_cuda(y, U, delta, AtAy, Atb, hyp)
+    B, P, n = y.shape
+    y_next = torch.empty_like(y)
+    U_next = torch.empty_like(y) if want_U else None
+    d_next = torch.empty_like(y) if want_delta else None
+    graw = torch.empty_like(y) if want_graw else None
+    cl = _lib.Clamps(*clamps)
+    h = _hyp_struct(hyp, B, P)
+    with device_guard(dev):
+        check(lib.dadmm_step_fwd(dtype_code(y), B, P, n, C.byref(graph.c), C.byref(cl), C.byref(h), ptr(y), ptr(U),
+                                 ptr(delta), ptr(AtAy), ptr(Atb), ptr(y_next), ptr(U_next), ptr(d_next), ptr(graw),
+                                 ptr(flags), stream_ptr(dev)), "dadmm_step_fwd")
+    return y_next, U_next, d_next, graw
+
+
+def step_bwd(graph: BatchGraph, clamps, hyp, y, U, delta, graw, y_next, gy_next, gU_next, gdelta_next,
+             per_sample: bool, label=None, loss_coef: float = 0.0):
+    """Backward of ``step_fwd``.  Returns (gy_direct, gAtAy, gU, gdelta, ghyp) with ghyp shaped like hyp."""
+    dev = require_cuda(y, U, graw, y_next)
+    B, P, n = y.shape
+    dt = dtype_code(y)
+    gy, ga, gU, gd = (torch.empty_like(y) for _ in range(4))
+    part = torch.empty(lib.dadmm_partials_elems(dt, B, P, n), dtype=y.dtype, device=dev)
+    cl = _lib.Clamps(*clamps)
+    h = _hyp_struct(hyp, B, P)
+    ghyp = torch.empty_like(hyp)
+    with device_guard(dev):
+        check(lib.dadmm_step_bwd(dt, B, P, n, C.byref(graph.c), C.byref(cl), C.byref(h), ptr(y), ptr(U), ptr(delta),
+                                 ptr(graw), ptr(y_next), ptr(gy_next), None, ptr(gU_next), ptr(gdelta_next),
+                                 ptr(label), float(loss_coef), ptr(gy), ptr(ga), ptr(gU), ptr(gd), ptr(part),
+                                 stream_ptr(dev)), "dadmm_step_bwd")
+        if per_sample:
+            check(lib.dadmm_reduce_hyp(dt, B, P, n, ptr(part), 1, ptr(ghyp), 4 * P, 1, P, 0, stream_ptr(dev)),
+                  "dadmm_reduce_hyp")
+        else:
+            check(lib.dadmm_reduce_hyp(dt, B, P, n, ptr(part), 0, ptr(ghyp), 0, 4, 1, 0, stream_ptr(dev)),
+                  "dadmm_reduce_hyp")
+    return gy, ga, gU, gd, ghyp
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------------
+class Contract(torch.autograd.Function):
+    """y [B,P,n] -> W y; backward Wt g (Wt = W^T, passed explicitly so no transpose is re-materialised)."""
+
+    @staticmethod
+    def forward(ctx, x, W, Wt, algo):
+        ctx.Wt, ctx.algo = Wt, algo
+        return contract(W, x, algo=algo)
+
+    @staticmethod
+    def backward(ctx, g):
+        return contract(ctx.Wt, g.contiguous(), algo=ctx.algo), None, None, None
+
+
+class Step(torch.autograd.Function):
+    """Differentiable single iteration (model #3: the hypernetwork sits between iterations).
+    Inputs y, U, delta, AtAy, Atb [B,P,n]; hyp [B,4,P] or [P,4].  Outputs (y+, U+, delta+)."""
+
+    @staticmethod
+    def forward(ctx, y, U, delta, AtAy, Atb, hyp, graph, clamps, flags):
+        y, U, delta, AtAy, Atb, hyp = (t.contiguous() for t in (y, U, delta, AtAy, Atb, hyp))
+        y_next, U_next, d_next, graw = step_fwd(graph, clamps, hyp, y, U, delta, AtAy, Atb, flags=flags)
+        ctx.graph, ctx.clamps = graph, clamps
+        ctx.save_for_backward(y, U, delta, graw, y_next, hyp)
+        return y_next, U_next, d_next
+
+    @staticmethod
+    def backward(ctx, gy_next, gU_next, gd_next):
+        y, U, delta, graw, y_next, hyp = ctx.saved_tensors
+        c = lambda t: None if t is None else t.contiguous()
+        gy, ga, gU, gd, ghyp = step_bwd(ctx.graph, ctx.clamps, hyp, y, U, delta, graw, y_next, c(gy_next), c(gU_next),
+                                        c(gd_next), per_sample=(hyp.dim() == 3))
+        return gy, gU, gd, ga, None, ghyp, None, None, None
+
+
+class Unfolded(torch.autograd.Function):
+    """K fused iterations of model #1: hyp [K,P,4] -> Y [K,B,P,n].  Saves Y, U_k and the raw
+    gradients r_k; backward runs the reverse sweep on device and returns d/d hyp only (the
+    reference has no other differentiable input on this path)."""
+
+    @staticmethod
+    def forward(ctx, hyp, W, Wt, Atb, y0, U0, d0, graph, clamps, algo, flags, handle):
+        dev = require_cuda(hyp, W, Atb, y0, U0, d0)
+        hyp, Atb, y0, U0, d0 = (t.contiguous() for t in (hyp, Atb, y0, U0, d0))
+        K, P, _ = hyp.shape
+        B, _, n = y0.shape
+        dt, al = dtype_code(y0), _algo(algo)
+        need_grad = ctx.needs_input_grad[0]
+        Y = torch.empty((K, B, P, n, 1), dtype=y0.dtype, device=dev)
+        U_save = torch.empty((max(K - 1, 1), B, P, n), dtype=y0.dtype, device=dev) if need_grad else None
+        R_save = torch.empty((K, B, P, n), dtype=y0.dtype, device=dev) if need_grad else None
+        carr = _clamps_array(clamps)
+        with device_guard(dev):
+            wsb = lib.dadmm_unfolded_ws_bytes(dt, al, B, P, n, K, 0)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            check(lib.dadmm_unfolded_fwd(dt, al, B, P, n, K, C.byref(graph.c), carr, ptr(hyp), ptr(W), ptr(Atb), ptr(y0),
+                                         ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(ws), wsb, ptr(flags),
+                                         stream_ptr(dev)), "dadmm_unfolded_fwd")
+        if need_grad:
+            ctx.save_for_backward(hyp, Wt, y0, U0, d0, Y, U_save, R_save)
+            ctx.graph, ctx.clamps, ctx.algo = graph, carr, al
+            ctx.handle = handle
+        return Y
+
+    @staticmethod
+    def backward(ctx, gY):
+        hyp, Wt, y0, U0, d0, Y, U_save, R_save = ctx.saved_tensors
+        dev = Y.device
+        K, B, P, n = Y.shape[:4]
+        dt = dtype_code(Y)
+        label, coef = None, None
+        fused = ctx.handle.take() if ctx.handle is not None else None
+        if fused is not None:
+            label, coefs, sentinel = fused
+            coef = (C.c_double * K)(*coefs)
+            if gY is not None and gY.data_ptr() == sentinel.data_ptr():
+                gY = None       # zero placeholder emitted by MSELoss.backward: gradient arrives through (label, coef)
+        if gY is not None:
+            gY = gY.contiguous()
+        ghyp = torch.empty_like(hyp)
+        with device_guard(dev):
+            wsb = lib.dadmm_unfolded_ws_bytes(dt, ctx.algo, B, P, n, K, 1)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            check(lib.dadmm_unfolded_bwd(dt, ctx.algo, B, P, n, K, C.byref(ctx.graph.c), ctx.clamps, ptr(hyp), ptr(Wt),
+                                         ptr(y0), ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(gY),
+                                         ptr(label), coef, ptr(ghyp), ptr(ws), wsb, stream_ptr(dev)),
+                  "dadmm_unfolded_bwd")
+        return (ghyp,) + (None,) * 11
+
+
+def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[int] = None) -> torch.Tensor:
+    """losses[k] = sum (Y[k]-label)^2 / (P*B_norm*n)  (gnn_dlasso_utils.py:54-66).  No autograd."""
+    dev = require_cuda(Y, label)
+    K, B, P, n = Y.shape[:4]
+    Yc, lab = Y.contiguous(), label.contiguous()
+    dt = dtype_code(Yc)
+    losses = torch.empty(K, dtype=Y.dtype, device=dev)
+    with device_guard(dev):
+        wsb = lib.dadmm_loss_ws_bytes(dt, K, B, P, n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.dadmm_loss_fwd(dt, K, B, P, n, int(B_norm or B), ptr(Yc), ptr(lab), ptr(losses), ptr(ws), wsb,
+                                 stream_ptr(dev)), "dadmm_loss_fwd")
+    return losses
+
+
+class FusedLossHandle:
+    """Side channel between ``MSELoss.backward`` and ``Unfolded.backward`` (same autograd pass)."""
+
+    def __init__(self):
+        self.pending = None
+
+    def offer(self, label, coefs, sentinel) -> bool:
+        if self.pending is not None:
+            return False
+        self.pending = (label, coefs, sentinel)
+        return True
+
+    def take(self):
+        p, self.pending = self.pending, None
+        return p
+
+
+class MSELoss(torch.autograd.Function):
+    """Per-iteration losses [K] with a fused backward.
+
+    When Y comes straight from ``Unfolded`` (``Y._dadmm_handle`` set by the module), backward hands the
+    gradient to the reverse sweep as (label, coef[k]) -- the kernel synthesises
+    gY[k] = coef[k]*(Y[k]-label) on the fly -- and returns a stride-0 zero placeholder instead of a
+    dense [K,B,P,n] tensor.  Otherwise it materialises gY with ``dadmm_loss_bwd``."""
+
+    @staticmethod
+    def forward(ctx, Y, label, B_norm, handle):
+        ctx.save_for_backward(Y, label)
+        ctx.B_norm, ctx.handle = B_norm, handle
+        return loss_per_iteration(Y, label, B_norm)
+
+    @staticmethod
+    def backward(ctx, g_losses):
+        Y, label = ctx.saved_tensors
+        K, B, P, n = Y.shape[:4]
+        scale = 2.0 / (P * (ctx.B_norm or B) * n)
+        coefs = [float(v) * scale for v in g_losses.detach().to("cpu", torch.float64).tolist()]
+        if ctx.handle is not None:
+            sentinel = torch.zeros((), dtype=Y.dtype, device=Y.device).expand(Y.shape)
+            if ctx.handle.offer(label.contiguous(), coefs, sentinel):
+                return sentinel, None, None, None
+        gY = torch.empty_like(Y, memory_format=torch.contiguous_format)
+        with device_guard(Y.device):
+            check(lib.dadmm_loss_bwd(dtype_code(Y), K, B, P, n, ptr(Y.contiguous()), ptr(label.contiguous()),
+                                     (C.c_double * K)(*coefs), ptr(gY), stream_ptr(Y.device)), "dadmm_loss_bwd")
+        return gY, None, None, None

@@ -1,0 +1,172 @@
+/* dadmm.h -- C ABI of libdadmm_sm100.so: the B200 (sm_100a) hot path of the unfolded D-ADMM
+ * distributed-LASSO solver.
+ *
+ * Each entry point replaces a piece of the reference's Python hot loop (paths relative to the
+ * reference checkout; the reference has no FFI of its own -- its boundary is the nn.Module
+ * surface, mirrored by the Python modules next to this library):
+ *
+ *   dadmm_contract      <- unfolded_DLASSO.py:69-71 (AtAy[:,p] = AtA[0,p] @ y[:,p]),
+ *                          unfolded_DLASSO.py:120-124 (compute_Atx), and the matmul backward
+ *                          autograd derives from them
+ *   dadmm_step_fwd      <- unfolded_DLASSO.py:73-99 (grad assembly, clamps, primal update,
+ *                          compute_delta :127-140, dual update); model #3 variant
+ *                          gnn_dlasso_models_progressive.py:205-232
+ *   dadmm_step_bwd      <- the autograd backward of the same lines
+ *   dadmm_reduce_hyp    <- the sum-to-size reductions autograd performs for the broadcast
+ *                          hyper-parameters alpha,tau,rho,eta (unfolded_DLASSO.py:64-67)
+ *   dadmm_unfolded_fwd  <- the whole `for k in range(K)` loop, unfolded_DLASSO.py:53-107
+ *   dadmm_unfolded_bwd  <- loss.backward() through that loop (unfolded_train_new.py:79)
+ *   dadmm_loss_fwd/bwd  <- gnn_dlasso_utils.py:27-88 (compute_loss) and its backward
+ *
+ * Conventions: all data pointers are DEVICE pointers to contiguous arrays of `dtype`
+ * (DADMM_F32 / DADMM_F64) unless a stride is given; state tensors are [B,P,n] with n fastest
+ * (the reference's [B,P,n,1]); the caller owns every buffer (workspaces included: nothing is
+ * allocated here); calls are asynchronous on `stream` (a cudaStream_t); no global mutable
+ * state apart from the thread-local error string.  Return value: 0 success, <0 invalid
+ * argument, >0 a cudaError_t.  Nothing throws.
+ */
+#ifndef DADMM_H_
+#define DADMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DADMM_ABI_VERSION 1
+
+typedef void* dadmm_stream_t; /* cudaStream_t */
+
+enum { DADMM_F32 = 0, DADMM_F64 = 1 };
+
+/* contraction algorithms */
+enum {
+    DADMM_ALGO_AUTO = 0,      /* tcgen05 when the shape allows it (fp32 only), else SIMT          */
+    DADMM_ALGO_SIMT = 1,      /* FP32/FP64 FMA pipe, exact IEEE accumulation in k order           */
+    DADMM_ALGO_TC_3XTF32 = 2  /* tcgen05.mma kind::tf32, hi/lo split of both operands (3 MMAs)    */
+};
+
+/* non-finite bits OR-ed into `flags` by the step kernel (reference guards,
+ * unfolded_DLASSO.py:55-61,84-86,102-104) */
+enum { DADMM_FLAG_Y = 1, DADMM_FLAG_U = 2, DADMM_FLAG_GRAD = 4, DADMM_FLAG_YNEXT = 8 };
+
+/* Graphs of one batch: `n_graphs` distinct graphs over P nodes, de-duplicated on the host, plus a
+ * per-problem index.  For node q of graph g the "event list" ev_idx[ev_ptr[g*P+q] .. ev_ptr[g*P+q+1])
+ * holds neighbour ids in the exact order in which the reference's compute_delta
+ * (unfolded_DLASSO.py:132-139) accumulates (y_q - y_e) into delta[q]; every undirected edge appears
+ * twice per endpoint, so delta = 2*L*y with the reference's rounding. */
+typedef struct dadmm_graph {
+    int32_t n_graphs;
+    int32_t P;
+    const int32_t* ev_ptr;   /* device, [n_graphs*P + 1]                                   */
+    const int32_t* ev_idx;   /* device, [ev_ptr[n_graphs*P]]                               */
+    const int32_t* deg;      /* device, [n_graphs*P]: len(list(graph.neighbors(p)))        */
+    const int32_t* graph_id; /* device, [B], or NULL when every problem uses graph 0       */
+} dadmm_graph;
+
+/* element-wise clamp bounds of one iteration (unfolded_DLASSO.py:80-81,92-93,99;
+ * gnn_dlasso_models_progressive.py:212-232).  D = +inf disables the delta clamp. */
+typedef struct dadmm_clamps {
+    double G;  /* |grad|  */
+    double V;  /* |y|     */
+    double D;  /* |delta| */
+    double Uc; /* |U|     */
+} dadmm_clamps;
+
+/* strided view of the hyper-parameters (alpha,tau,rho,eta) = c 0..3 of agent p of problem b:
+ * ptr[b*stride_b + p*stride_p + c*stride_c].  Model #1 table row [P,4]: (0,4,1);
+ * model #3 per-sample [B,4,P]: (4P,1,P). */
+typedef struct dadmm_hyp {
+    const void* ptr;
+    int64_t stride_b, stride_p, stride_c;
+} dadmm_hyp;
+
+int dadmm_abi_version(void);
+const char* dadmm_last_error(void);
+/* 0 when the current CUDA device is an sm_100 part this library was built for */
+int dadmm_device_check(void);
+/* number of kernels launched by this library since load (all threads) */
+int64_t dadmm_launch_count(void);
+
+/* out[b,p,i] (+)= sum_k W[p,i,k] * x[b,p,k]  -- batched over agents, all tensors strided:
+ *   W  (p,i,k) -> W  + p*w_sp + i*w_si + k*w_sk      (i < n_out, k < n_in)
+ *   x  (b,p,k) -> x  + b*x_sb + p*x_sp + k*x_sk
+ *   out(b,p,i) -> out+ b*o_sb + p*o_sp + i*o_si
+ * ws/ws_bytes: scratch for DADMM_ALGO_TC_3XTF32 (see dadmm_contract_ws_bytes), may be NULL for SIMT. */
+int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in,
+                   const void* W, int64_t w_sp, int64_t w_si, int64_t w_sk,
+                   const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk,
+                   void* out, int64_t o_sb, int64_t o_sp, int64_t o_si,
+                   int accumulate, void* ws, size_t ws_bytes, dadmm_stream_t stream);
+size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in);
+/* 1 if dadmm_contract(algo) would run on tcgen05 for this call shape (contiguous [P,n,n]/[B,P,n]) */
+int dadmm_contract_uses_tensor_cores(int dtype, int algo, int B, int P, int n_out, int n_in);
+
+/* One D-ADMM iteration (all agents, all problems):
+ *   d    = delta ? delta : clampD(2L y)
+ *   r    = AtAy - Atb + sign(y)*tau + U*deg + d*rho            (left to right, each op rounded)
+ *   g    = clamp(r, +-G);  y+ = clamp(y - alpha*g, +-V)
+ *   d+   = clampD(2L y+);  U+ = clamp(U + d+*eta, +-Uc)
+ * y_next required; U_next, delta_next, grad_raw (r, saved for backward) and flags may be NULL
+ * (U_next == delta_next == NULL skips the consensus phase).  In-place (y_next==y, U_next==U) is allowed. */
+int dadmm_step_fwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,
+                   const dadmm_hyp* hyp, const void* y, const void* U, const void* delta,
+                   const void* AtAy, const void* Atb,
+                   void* y_next, void* U_next, void* delta_next, void* grad_raw,
+                   int32_t* flags, dadmm_stream_t stream);
+
+/* Backward of dadmm_step_fwd.  Incoming adjoints (each may be NULL = 0): gy_next_a + gy_next_b
+ * (+ loss_coef*(y_next - label[b,:]) when label != NULL) for y+, gU_next for U+, gdelta_next for d+.
+ * Outputs: gy = adjoint of y through the direct path only, gAtAy = adjoint of AtAy (the caller adds
+ * W^T gAtAy to gy with dadmm_contract), gU, gdelta (adjoint of the `delta` input; when the forward
+ * recomputed delta from y, feed it to the previous iteration as gdelta_next), and per-tile partial
+ * sums of d/d(alpha,tau,rho,eta) in `ghyp_partials` (dadmm_partials_elems() elements), to be
+ * finished by dadmm_reduce_hyp.  Outputs may alias the corresponding *_next inputs. */
+int dadmm_step_bwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,
+                   const dadmm_hyp* hyp, const void* y, const void* U, const void* delta,
+                   const void* grad_raw, const void* y_next,
+                   const void* gy_next_a, const void* gy_next_b, const void* gU_next, const void* gdelta_next,
+                   const void* label, double loss_coef,
+                   void* gy, void* gAtAy, void* gU, void* gdelta, void* ghyp_partials,
+                   dadmm_stream_t stream);
+size_t dadmm_partials_elems(int dtype, int B, int P, int n);
+
+/* ghyp(b?,p,c) (+)= sum over tiles (and over b when per_sample == 0) of the partials. */
+int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, int per_sample,
+                     void* ghyp, int64_t stride_b, int64_t stride_p, int64_t stride_c,
+                     int accumulate, dadmm_stream_t stream);
+
+/* K iterations of model #1 (hyp [K,P,4] shared over the batch, clamps[K] on the host):
+ * Y[k] = y_{k+1}; U_save[k] = U_{k+1} and R_save[k] = r_k are written when non-NULL (training).
+ * W = AtA [P,n,n].  ws >= dadmm_unfolded_ws_bytes(). */
+int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                       const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb,
+                       const void* y0, const void* U0, const void* d0,
+                       void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
+                       int32_t* flags, dadmm_stream_t stream);
+/* Reverse sweep: gY [K,B,P,n] dense upstream gradient (may be NULL) and/or the fused loss term
+ * loss_coef[k]*(Y[k]-label) (label [B,n], loss_coef host [K], both may be NULL).  Wt = AtA^T [P,n,n].
+ * Writes ghyp [K,P,4]. */
+int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                       const dadmm_clamps* clamps, const void* hyp, const void* Wt,
+                       const void* y0, const void* U0, const void* d0,
+                       const void* Y, const void* U_save, const void* R_save,
+                       const void* gY, const void* label, const double* loss_coef,
+                       void* ghyp, void* ws, size_t ws_bytes, dadmm_stream_t stream);
+size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward);
+
+/* losses[k] = sum_{b,p,i} (Y[k,b,p,i] - label[b,i])^2 / (P*B_norm*n)  (gnn_dlasso_utils.py:54-66;
+ * B_norm = global batch when the batch is sharded over ranks).  ws >= dadmm_loss_ws_bytes(). */
+int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const void* Y, const void* label,
+                   void* losses, void* ws, size_t ws_bytes, dadmm_stream_t stream);
+/* gY[k] = coef[k] * (Y[k] - label)   (coef on the host, [K]; zero rows are memset) */
+int dadmm_loss_bwd(int dtype, int K, int B, int P, int n, const void* Y, const void* label,
+                   const double* coef, void* gY, dadmm_stream_t stream);
+size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DADMM_H_ */

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libdadmm_sm100.so) against the CPU oracle and the
+golden vectors minted from the reference.  Tolerances (north_star: 1e-5 relative in fp32):
+  * element-wise / consensus arithmetic given identical inputs ............ bit-exact
+  * teacher-forced single step with our own contraction ................... rel-L2 <= 1e-5
+  * K-step trajectories vs the fp64 reference .............................. err <= max(1e-5, 2*err_ref32)
+    (the reference's own fp32 run is that far from its fp64 run; SURVEY.md 8c protocol)
+  * fp64 instantiation of the same kernels ................................. <= 1e-9
+"""
+import math
+
+import pytest
+import torch
+
+from helpers import MODEL1_CASES, MODEL3_CASES, Golden, rel_l2, random_problem
+from oracle import dadmm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _df():
+    from dadmm_b200 import functional as DF
+    from dadmm_b200.graph import BatchGraph
+    return DF, BatchGraph
+
+
+def _hyp_for(g, dtype=torch.float32):
+    hyp = O.hyp_table(g.t("param", dtype), g.t("max_param", dtype), bool(g.z["training"]))
+    return hyp.expand(-1, g.P, -1).contiguous() if hyp.shape[1] == 1 else hyp
+
+
+def _dev(t):
+    return t.squeeze(-1).contiguous().to(DEV) if t.dim() == 4 else t.contiguous().to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ contraction
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float64, 1e-13)])
+@pytest.mark.parametrize("B,P,n_out,n_in", [(32, 5, 500, 500), (7, 3, 51, 51), (130, 2, 129, 64), (1, 1, 1, 1), (257, 4, 256, 256)])
+def test_contract_vs_fp64(dtype, tol, B, P, n_out, n_in):
+    DF, _ = _df()
+    gen = torch.Generator().manual_seed(B * 1000 + n_out)
+    W = torch.randn((P, n_out, n_in), generator=gen, dtype=torch.float64)
+    x = torch.randn((B, P, n_in), generator=gen, dtype=torch.float64)
+    ref = torch.einsum("pik,bpk->bpi", W, x)
+    out = DF.contract(W.to(dtype).to(DEV), x.to(dtype).to(DEV), algo="simt")
+    ref_in = torch.einsum("pik,bpk->bpi", W.to(dtype).double(), x.to(dtype).double())
+    assert rel_l2(out.cpu(), ref_in) < tol
+    acc = DF.contract(W.to(dtype).to(DEV), x.to(dtype).to(DEV), out=out.clone(), accumulate=True, algo="simt")
+    assert rel_l2(acc.cpu(), 2 * ref_in) < tol
+    assert rel_l2(out.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_atx_matches_reference_ops(name):
+    """compute_Atx (unfolded_DLASSO.py:120-124) for x = b (c=1) and x = A (c=n, AtA)."""
+    DF, _ = _df()
+    g = Golden(name)
+    A, b = g.t("A"), g.t("b")
+    assert rel_l2(DF.atx(A.to(DEV), b.to(DEV)).cpu(), O.atx(A.double(), b.double())) < 2e-6
+    assert rel_l2(DF.atx(A.to(DEV), A.to(DEV)).cpu(), O.atx(A.double(), A.double())) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ single step
+def _trace(g, dtype, clamp_fn=O.clamps_model1, hyp=None):
+    A = g.t("A", dtype)
+    AtA, Atb = O.atx(A, A), O.atx(A, g.t("b", dtype))
+    hyp = _hyp_for(g, dtype) if hyp is None else hyp
+    Y, tr = O.unfolded_forward(AtA, Atb, g.graphs, g.t("y0", dtype), g.t("U0", dtype), g.t("d0", dtype), hyp,
+                               clamp_fn=clamp_fn, exact_delta=True, keep=True)
+    return AtA, Atb, hyp, Y, tr
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_step_fwd_teacher_forced_bit_exact(name):
+    """Given the oracle's own (y,U,delta,AtAy) the fused step must reproduce y+, U+, delta+ and the raw
+    gradient BIT FOR BIT (same op order, one rounding per op, reference accumulation order in delta)."""
+    DF, BG = _df()
+    g = Golden(name)
+    AtA, Atb, hyp, Y, tr = _trace(g, torch.float32)
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    for k, t in enumerate(tr):
+        c = O.clamps_model1(k)
+        yn, Un, dn, graw = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hyp[k].contiguous().to(DEV), _dev(t["y"]), _dev(t["U"]),
+                                       _dev(t["delta"]), _dev(t["AtAy"]), _dev(Atb))
+        for ours, ref, what in ((yn, t["y_next"], "y"), (Un, t["U_next"], "U"), (dn, t["delta_next"], "delta"),
+                                (graw, t["grad_raw"], "grad")):
+            assert torch.equal(ours.cpu(), ref.squeeze(-1)), f"{what} differs at k={k}: {float((ours.cpu() - ref.squeeze(-1)).abs().max())}"
+        if k > 0:   # delta recomputed in-kernel from y_k must equal the stored delta_k
+            yn2, Un2, _, _ = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hyp[k].contiguous().to(DEV), _dev(t["y"]),
+                                         _dev(t["U"]), None, _dev(t["AtAy"]), _dev(Atb))
+            assert torch.equal(yn2, yn) and torch.equal(Un2, Un)
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_step_fwd_teacher_forced_own_contraction(name):
+    """Strict gate: single step with OUR contraction kernel, rel-L2 <= 1e-5 on every output."""
+    DF, BG = _df()
+    g = Golden(name)
+    AtA, Atb, hyp, Y, tr = _trace(g, torch.float32)
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    W = AtA[0].contiguous().to(DEV)
+    for k, t in enumerate(tr):
+        c = O.clamps_model1(k)
+        a = DF.contract(W, _dev(t["y"]))
+        assert rel_l2(a.cpu(), t["AtAy"].squeeze(-1)) < 1e-5
+        yn, Un, dn, graw = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hyp[k].contiguous().to(DEV), _dev(t["y"]), _dev(t["U"]),
+                                       _dev(t["delta"]), a, _dev(Atb))
+        assert rel_l2(yn.cpu(), t["y_next"].squeeze(-1)) < 1e-5
+        assert rel_l2(Un.cpu(), t["U_next"].squeeze(-1)) < 1e-5
+        assert rel_l2(dn.cpu(), t["delta_next"].squeeze(-1)) < 1e-5
+
+
+def _oracle_step_grads(g, t, hyp_k, clamps, dtype, gy, gU, gd, per_sample):
+    """Autograd of the oracle's single step wrt (y, U, delta, hyp) for upstream (gy, gU, gd)."""
+    P = g.P
+    lap2 = O.laplacian2(g.graphs, P, dtype)
+    deg = O.degrees(g.graphs, P, dtype)
+    A = g.t("A", dtype)
+    AtA, Atb = O.atx(A, A), O.atx(A, g.t("b", dtype))
+    y, U, d = (t[k].clone().requires_grad_(True) for k in ("y", "U", "delta"))
+    h = hyp_k.clone().requires_grad_(True)
+    if per_sample:
+        al, ta, rh, et = (h[:, i].reshape(-1, P, 1, 1) for i in range(4))       # h [B,4,P]
+    else:
+        al, ta, rh, et = (h[:, i].reshape(1, P, 1, 1) for i in range(4))        # h [P,4]
+    yn, Un, dn, _ = O.step(O.contract(AtA, y), Atb, deg, y, U, d, al, ta, rh, et, clamps, lambda v: O.delta_dense(lap2, v))
+    (yn * gy).sum().add((Un * gU).sum()).add((dn * gd).sum()).backward()
+    return y.grad, U.grad, d.grad, h.grad
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-5)])
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_step_bwd_teacher_forced(name, dtype, tol):
+    DF, BG = _df()
+    g = Golden(name)
+    AtA, Atb, hyp, Y, tr = _trace(g, dtype)
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    W = AtA[0].contiguous().to(DEV)
+    Wt = W.transpose(1, 2).contiguous()
+    gen = torch.Generator().manual_seed(3)
+    for k in (0, len(tr) // 2, len(tr) - 1):
+        t = tr[k]
+        c = O.clamps_model1(k)
+        gy, gU, gd = (torch.randn(t["y"].shape, generator=gen, dtype=dtype) for _ in range(3))
+        ry, rU, rd, rh = _oracle_step_grads(g, t, hyp[k], c, dtype, gy, gU, gd, per_sample=False)
+        a = DF.contract(W, _dev(t["y"]))
+        _, _, _, graw = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hyp[k].contiguous().to(DEV), _dev(t["y"]), _dev(t["U"]),
+                                    _dev(t["delta"]), a, _dev(Atb))
+        oy, oa, oU, od, oh = DF.step_bwd(graph, (c.G, c.V, c.D, c.Uc), hyp[k].contiguous().to(DEV), _dev(t["y"]), _dev(t["U"]),
+                                         _dev(t["delta"]), graw, _dev(t["y_next"]), _dev(gy), _dev(gU), _dev(gd),
+                                         per_sample=False)
+        oy = oy + DF.contract(Wt, oa)
+        assert rel_l2(oy.cpu(), ry.squeeze(-1)) < tol, k
+        assert rel_l2(oU.cpu(), rU.squeeze(-1)) < tol, k
+        assert rel_l2(od.cpu(), rd.squeeze(-1)) < tol, k
+        assert rel_l2(oh.cpu(), rh) < 10 * tol, k
+
+
+# ------------------------------------------------------------------------------------------ K iterations
+def _run_unfolded(g, dtype, algo="auto", clamp_fn=None, hyp=None, need_grad=True):
+    DF, BG = _df()
+    A = g.t("A", dtype)
+    AtA, Atb = O.atx(A, A), O.atx(A, g.t("b", dtype))
+    W = AtA[0].contiguous().to(DEV)
+    Wt = W.transpose(1, 2).contiguous()
+    hyp = (_hyp_for(g, dtype) if hyp is None else hyp).to(DEV).requires_grad_(need_grad)
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    clamps = [(clamp_fn or DF.clamps_model1)(k) for k in range(hyp.shape[0])]
+    flags = torch.zeros(hyp.shape[0], dtype=torch.int32, device=DEV)
+    Y = DF.Unfolded.apply(hyp, W, Wt, _dev(Atb), _dev(g.t("y0", dtype)), _dev(g.t("U0", dtype)), _dev(g.t("d0", dtype)),
+                          graph, clamps, algo, flags, None)
+    assert not bool(flags.any())
+    return Y, hyp
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_unfolded_forward_k_step_gate(name):
+    g = Golden(name)
+    Y, _ = _run_unfolded(g, torch.float32, need_grad=False)
+    Y = Y.cpu()
+    Y64, Yref = g.t("Y64"), g.t("Y")
+    for k in range(g.K):
+        ours, ref = rel_l2(Y[k], Y64[k]), rel_l2(Yref[k], Y64[k])
+        assert ours <= max(1e-5, 2 * ref), (k, ours, ref)
+    lm, lf = O.loss(Y, g.t("label"))
+    assert math.isclose(float(lf), float(g.z["loss_final"]), rel_tol=1e-5)
+    assert math.isclose(float(lm), float(g.z["loss_mean"]), rel_tol=1e-5)
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_unfolded_fp64_proves_algebra(name):
+    g = Golden(name)
+    dt = torch.float64
+    param = g.t("param", dt).clone().requires_grad_(True)
+    table = O.hyp_table(param, g.t("max_param", dt), bool(g.z["training"]))
+    hyp = table.expand(-1, g.P, -1).contiguous()
+    Y, hyp_dev = _run_unfolded(g, dt, hyp=hyp.detach())
+    assert rel_l2(Y.cpu(), g.t("Y64")) < 1e-9
+    DF, _ = _df()
+    losses = DF.MSELoss.apply(Y, g.t("label", dt).to(DEV), None, None)
+    assert math.isclose(float(losses[-1]) + 1e-8, float(g.z["loss_final64"]), rel_tol=1e-9)
+    losses[-1].backward()
+    hyp.backward(hyp_dev.grad.cpu())
+    assert rel_l2(param.grad, g.t("dparam64")) < 1e-7
+
+
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_unfolded_fp32_gradient_gate(name):
+    g = Golden(name)
+    DF, _ = _df()
+    param = g.t("param").clone().requires_grad_(True)
+    table = O.hyp_table(param, g.t("max_param"), bool(g.z["training"]))
+    hyp = table.expand(-1, g.P, -1).contiguous()
+    Y, hyp_dev = _run_unfolded(g, torch.float32, hyp=hyp.detach())
+    losses = DF.MSELoss.apply(Y, g.t("label").to(DEV), None, None)
+    losses[-1].backward()
+    hyp.backward(hyp_dev.grad.cpu())
+    ours, ref = rel_l2(param.grad, g.t("dparam64")), rel_l2(g.t("dparam"), g.t("dparam64"))
+    assert ours <= max(1e-5, 2 * ref), (ours, ref)
+
+
+@pytest.mark.parametrize("name", MODEL3_CASES)
+def test_model3_recurrence_frozen_hyp(name):
+    """Model #3 clamps (G=10, V=100, delta +-20, U +-100) with per-sample hyper-parameters, step by step."""
+    DF, BG = _df()
+    g = Golden(name)
+    hyp = g.t("hyp")                                                   # [K,B,P,4]
+    AtA, Atb, _, Y, tr = _trace(g, torch.float32, clamp_fn=O.clamps_model3, hyp=hyp)
+    assert torch.equal(Y, g.t("Y"))
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    c = O.clamps_model3()
+    for k, t in enumerate(tr):
+        hs = hyp[k].permute(0, 2, 1).contiguous().to(DEV)              # [B,4,P]
+        yn, Un, dn, _ = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hs, _dev(t["y"]), _dev(t["U"]), _dev(t["delta"]),
+                                    _dev(t["AtAy"]), _dev(Atb))
+        assert torch.equal(yn.cpu(), t["y_next"].squeeze(-1))
+        assert torch.equal(Un.cpu(), t["U_next"].squeeze(-1))
+        assert torch.equal(dn.cpu(), t["delta_next"].squeeze(-1))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-5)])
+def test_model3_step_bwd_per_sample(dtype, tol):
+    DF, BG = _df()
+    g = Golden(MODEL3_CASES[0])
+    hyp = g.t("hyp", dtype)
+    AtA, Atb, _, Y, tr = _trace(g, dtype, clamp_fn=O.clamps_model3, hyp=hyp)
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    W = AtA[0].contiguous().to(DEV)
+    c = O.clamps_model3()
+    gen = torch.Generator().manual_seed(5)
+    t = tr[-1]
+    # scale delta up so that the +-20 clamp is active for some elements
+    gy, gU, gd = (torch.randn(t["y"].shape, generator=gen, dtype=dtype) for _ in range(3))
+    hs = hyp[-1].permute(0, 2, 1).contiguous()
+    ry, rU, rd, rh = _oracle_step_grads(g, t, hs, c, dtype, gy, gU, gd, per_sample=True)
+    a = DF.contract(W, _dev(t["y"]))
+    _, _, _, graw = DF.step_fwd(graph, (c.G, c.V, c.D, c.Uc), hs.to(DEV), _dev(t["y"]), _dev(t["U"]), _dev(t["delta"]), a, _dev(Atb))
+    oy, oa, oU, od, oh = DF.step_bwd(graph, (c.G, c.V, c.D, c.Uc), hs.to(DEV), _dev(t["y"]), _dev(t["U"]), _dev(t["delta"]),
+                                     graw, _dev(t["y_next"]), _dev(gy), _dev(gU), _dev(gd), per_sample=True)
+    oy = oy + DF.contract(W.transpose(1, 2).contiguous(), oa)
+    assert rel_l2(oy.cpu(), ry.squeeze(-1)) < tol
+    assert rel_l2(oU.cpu(), rU.squeeze(-1)) < tol
+    assert rel_l2(od.cpu(), rd.squeeze(-1)) < tol
+    assert rel_l2(oh.cpu(), rh) < 10 * tol
+
+
+# ------------------------------------------------------------------------------------------ size-independent properties
+def test_properties_at_scale():
+    """P=20, n=256, K=5, B=512 (config-3 shapes at 1/8 batch): clamp bounds hold, the run is bit-reproducible,
+    consensus sums to zero over agents, contraction is linear."""
+    DF, BG = _df()
+    P, n, m, K, B = 20, 256, 64, 5, 512
+    pr = random_problem(P, n, m, B, K, seed=11, a_scale=1.0)
+    A = pr["A"].to(DEV)
+    W = DF.atx(A, A)[0].contiguous()
+    Atb = DF.atx(A, pr["b"].to(DEV)).squeeze(-1)
+    graph = BG.from_graph_list(pr["graphs"], P, DEV)
+    hyp = O.hyp_table(pr["param"], torch.tensor([0.1, 0.99, 0.99, 0.99]), True).to(DEV)
+    clamps = [DF.clamps_model1(k) for k in range(K)]
+    run = lambda: DF.Unfolded.apply(hyp, W, W.transpose(1, 2).contiguous(), Atb, _dev(pr["y0"]), _dev(pr["U0"]),
+                                    _dev(pr["d0"]), graph, clamps, "auto", None, None)
+    Y1, Y2 = run(), run()
+    assert torch.equal(Y1, Y2)
+    for k in range(K):
+        assert float(Y1[k].abs().max()) <= clamps[k][1]
+    y = Y1[-1].squeeze(-1)
+    zero = torch.zeros_like(y)
+    inf = float("inf")
+    _, _, d, _ = DF.step_fwd(graph, (inf, inf, inf, inf), torch.zeros((P, 4), device=DEV), y, zero, zero, zero, zero,
+                             want_U=False, want_graw=False)
+    assert float(d.sum(dim=1).abs().max()) <= 1e-4 * float(d.abs().max())
+    x1, x2 = torch.randn_like(y), torch.randn_like(y)
+    lhs = DF.contract(W, 2 * x1 + x2)
+    rhs = 2 * DF.contract(W, x1) + DF.contract(W, x2)
+    assert rel_l2(lhs.cpu(), rhs.cpu()) < 1e-5
