@@ -86,8 +86,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) contract_simt_kernel(co
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int PAD = 4;
     constexpr int GM = TM / 4, GN = TN / 4;  // groups of 4 consecutive outputs per thread
-    __shared__ __align__(16) T As[2][BK][BM + PAD];
-    __shared__ __align__(16) T Bs[2][BK][BN + PAD];
+    __shared__ __align__(32) T As[2][BK][BM + PAD];
+    __shared__ __align__(32) T Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x;
     const int tx = tid % (BM / TM), ty = tid / (BM / TM);
     const int i0 = blockIdx.x * BM, b0 = blockIdx.y * BN, ag = blockIdx.z;
@@ -192,6 +192,7 @@ template <typename T, int WMODE, int XMODE>
 int launch_contract_simt_modes(const GemmParams<T>& p, cudaStream_t s) {
     using C = SimtCfg<T>;
     dim3 grid(ceil_div(p.M, C::BM), ceil_div(p.B, C::BN), p.P);
+    ProfScope prof(PROF_CONTRACT_SIMT, s);
     contract_simt_kernel<T, C::BM, C::BN, C::BK, C::TM, C::TN, WMODE, XMODE>
         <<<grid, (C::BM / C::TM) * (C::BN / C::TN), 0, s>>>(p);
     DADMM_LAUNCHED();

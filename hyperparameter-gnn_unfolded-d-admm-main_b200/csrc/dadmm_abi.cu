@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "contract_simt.cuh"
@@ -14,6 +16,31 @@
 namespace dadmm {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------------------------------
+// per-kind kernel timing
+// ------------------------------------------------------------------------------------------
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static thread_local int g_prof_open = -1;
+
+void prof_begin(int kind, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfRec r{kind, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    g_prof_open = (int)g_prof.size() - 1;
+}
+void prof_end(cudaStream_t s) {
+    if (!g_prof_on || g_prof_open < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_open < (int)g_prof.size()) cudaEventRecord(g_prof[g_prof_open].b, s);
+    g_prof_open = -1;
+}
 
 // ------------------------------------------------------------------------------------------
 // tile configuration of the step kernels
@@ -81,6 +108,7 @@ static int check_graph(const dadmm_graph* g, int P) {
 template <typename T, int VEC>
 static int launch_step_fwd_t(const StepFwdParams<T>& p, const StepCfg& c, cudaStream_t s) {
     if (int e = allow_smem(step_fwd_kernel<T, VEC>, c.smem_fwd)) return e;
+    ProfScope prof(PROF_STEP_FWD, s);
     step_fwd_kernel<T, VEC><<<c.grid, kStepThreads, c.smem_fwd, s>>>(p);
     DADMM_LAUNCHED();
     return 0;
@@ -88,6 +116,7 @@ static int launch_step_fwd_t(const StepFwdParams<T>& p, const StepCfg& c, cudaSt
 template <typename T, int VEC>
 static int launch_step_bwd_t(const StepBwdParams<T>& p, const StepCfg& c, cudaStream_t s) {
     if (int e = allow_smem(step_bwd_kernel<T, VEC>, c.smem_bwd)) return e;
+    ProfScope prof(PROF_STEP_BWD, s);
     step_bwd_kernel<T, VEC><<<c.grid, kStepThreads, c.smem_bwd, s>>>(p);
     DADMM_LAUNCHED();
     return 0;
@@ -157,6 +186,7 @@ static size_t partials_elems(int B, int P, int n) { return (size_t)((n + 31) / 3
 template <typename T>
 static int reduce_hyp_impl(int dtype, int B, int P, int n, const void* partials, int per_sample, void* ghyp,
                            int64_t sb, int64_t sp, int64_t sc, int accumulate, int nchunks, cudaStream_t s) {
+    ProfScope prof(PROF_REDUCE_HYP, s);
     if (per_sample) {
         const long long tot = (long long)B * P;
         reduce_hyp_sample_kernel<T><<<(unsigned)ceil_div64(tot, 256), 256, 0, s>>>((const T*)partials, nchunks, B, P,
@@ -210,6 +240,34 @@ extern "C" {
 int dadmm_abi_version(void) { return DADMM_ABI_VERSION; }
 const char* dadmm_last_error(void) { return g_err; }
 int64_t dadmm_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dadmm_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int dadmm_profile_read(double* ms_by_kind, int64_t* launches_by_kind) {
+    if (!ms_by_kind || !launches_by_kind) DADMM_FAIL(-1, "profile_read: null pointer");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int k = 0; k < PROF_KINDS; ++k) {
+        ms_by_kind[k] = 0;
+        launches_by_kind[k] = 0;
+    }
+    for (auto& r : g_prof) {
+        DADMM_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0;
+        DADMM_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_by_kind[r.kind] += ms;
+        launches_by_kind[r.kind] += 1;
+    }
+    return 0;
+}
 
 int dadmm_device_check(void) {
     int dev = 0, major = 0, minor = 0;
@@ -386,6 +444,7 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
     const int nblk = (int)std::min<long long>(1024, ceil_div64(per_k, 256 * 4));
     const double inv = 1.0 / ((double)P * (double)B_norm * (double)n);
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PROF_LOSS, s);
     if (dtype == DADMM_F32) {
         loss_partial_kernel<float><<<dim3(nblk, K), 256, 0, s>>>((const float*)Y, (const float*)label, B, P, n, (double*)ws);
         DADMM_LAUNCHED();

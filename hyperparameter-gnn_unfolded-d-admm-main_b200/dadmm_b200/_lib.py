@@ -50,6 +50,8 @@ def _load():
         "dadmm_last_error": (C.c_char_p, []),
         "dadmm_device_check": (i32, []),
         "dadmm_launch_count": (i64, []),
+        "dadmm_profile_enable": (i32, [i32]),
+        "dadmm_profile_read": (i32, [C.POINTER(dbl), C.POINTER(i64)]),
         "dadmm_contract": (i32, [i32, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
                                  i32, vp, sz, vp]),
         "dadmm_contract_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
@@ -134,3 +136,17 @@ def stream_ptr(dev) -> C.c_void_p:
 
 def launch_count() -> int:
     return int(lib.dadmm_launch_count())
+
+
+PROF_KINDS = ("contract_simt", "contract_tc", "step_fwd", "step_bwd", "reduce_hyp", "loss")
+
+
+def profile_enable(on: bool = True):
+    check(lib.dadmm_profile_enable(int(on)), "dadmm_profile_enable")
+
+
+def profile_read():
+    """{kind: (total_ms, launches)} accumulated since profile_enable(True)."""
+    ms, cnt = (C.c_double * 8)(), (C.c_int64 * 8)()
+    check(lib.dadmm_profile_read(ms, cnt), "dadmm_profile_read")
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(PROF_KINDS)}

@@ -90,6 +90,12 @@ int dadmm_device_check(void);
 /* number of kernels launched by this library since load (all threads) */
 int64_t dadmm_launch_count(void);
 
+/* Per-kernel-kind timing for bench.py's roofline: after dadmm_profile_enable(1) every launch is bracketed
+ * by CUDA events on its stream; dadmm_profile_read sums elapsed ms / launch counts per kind
+ * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss; arrays of 8). */
+int dadmm_profile_enable(int on);
+int dadmm_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
+
 /* out[b,p,i] (+)= sum_k W[p,i,k] * x[b,p,k]  -- batched over agents, all tensors strided:
  *   W  (p,i,k) -> W  + p*w_sp + i*w_si + k*w_sk      (i < n_out, k < n_in)
  *   x  (b,p,k) -> x  + b*x_sb + p*x_sp + k*x_sk
