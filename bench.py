@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- unfolded D-ADMM iterations*problems/s (fwd+bwd) on N B200s, against the kernel roofline, with
+the reference's CPU cost timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|cfg1|tiny]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one training step of model #1 (DLASSO_unfolded) on one synthetic batch: forward through all K
+unfolded iterations, compute_loss, loss_final.backward() through all K iterations, gradient all-reduce over
+ranks (N>1) and the Adam update of seq_hyp.param.  Default workload = BASELINE.json configs[3]
+(P=50, n=1024, m=256, K=25, global batch 4096 sharded over the ranks: strong scaling).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "hyperparameter-gnn_unfolded-d-admm-main_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import networkx as nx  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "unfolded D-ADMM iterations*problems/sec (fwd+bwd)"
+UNIT = "iter*problems/s"
+
+WORKLOADS = {
+    # name: P, n, m, K, B (global), graph_prob, B_ref (problems in one CPU-baseline sample)
+    "cfg4": dict(P=50, n=1024, m=256, K=25, B=4096, graph_prob=0.12, B_ref=4,
+                 desc="BASELINE configs[3]: P=50 agents, n=1024, m=256, K=25, global batch 4096, ER p=0.12 bridged, fresh graph per problem"),
+    "cfg3": dict(P=20, n=256, m=64, K=25, B=4096, graph_prob=0.5, B_ref=16,
+                 desc="BASELINE configs[2]: P=20, n=256, m=64, K=25, batch 4096, ER p=0.5, fresh graph per problem"),
+    "cfg1": dict(P=5, n=500, m=100, K=15, B=32, graph_prob=0.5, B_ref=32,
+                 desc="BASELINE configs[0]: P=5, n=500, m=100, K=15, batch 32, one shared ER p=0.5 graph"),
+    "tiny": dict(P=5, n=64, m=16, K=4, B=16, graph_prob=0.5, B_ref=4, desc="smoke-sized"),
+}
+
+
+def bridged_er(P, prob, seed):
+    """Per-problem graph recipe of the reference driver (gnn_dlasso_progressive.py:181-191), seeded."""
+    g = nx.erdos_renyi_graph(P, prob, seed=seed)
+    if not nx.is_connected(g):
+        comps = list(nx.connected_components(g))
+        for c in range(len(comps) - 1):
+            g.add_edge(list(comps[c])[0], list(comps[c + 1])[0])
+    return g
+
+
+def make_args(w):
+    return argparse.Namespace(m=w["m"], n=w["n"], P=w["P"], GHN_iter_num=w["K"], DADMM_mode="diff", alpha_max=0.1,
+                              tau_max=0.99, rho_max=0.99, eta_max=0.99, max_penalty_threshold=0.8,
+                              penalty_reduction_factor=0.95, batch_size=w["B"], snr=4, graph_prob=w["graph_prob"])
+
+
+def make_problem(w, B, lo=0, shared_graph=False):
+    """Synthetic inputs in the reference's format: A via set_A (seed 0), labels/observations via the
+    set_Data recipe, graphs seeded by the GLOBAL problem index (so shards of a batch see the same graphs)."""
+    import gnn_dlasso_utils
+    args = make_args(w)
+    torch.manual_seed(0)
+    A = gnn_dlasso_utils.set_A(args)
+    gen = torch.Generator().manual_seed(1000 + lo)
+    label = 2 * torch.randn((B, w["n"], 1), generator=gen) * (torch.rand((B, w["n"], 1), generator=gen) <= 0.25)
+    if shared_graph:
+        graphs = [bridged_er(w["P"], w["graph_prob"], 0)] * B
+    else:
+        graphs = [bridged_er(w["P"], w["graph_prob"], lo + i) for i in range(B)]
+    gen = torch.Generator().manual_seed(5)
+    param = torch.randn((w["K"], w["P"], 4), generator=gen) * 0.3
+    return args, A, label, graphs, param
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's loop-faithful port of the reference (the Python reference cannot travel to the
+# GPU box; oracle/dadmm_oracle.py::reference_port_fwd_bwd keeps its cost model: per-agent matmul loops,
+# Python neighbour loops with in-place slice updates, autograd over all of it)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(w, B_ref=None):
+    from oracle import dadmm_oracle as O
+    B_ref = B_ref or w["B_ref"]
+    args, A, label, graphs, param = make_problem(w, B_ref)
+    b = torch.stack([A[0, p] @ label for p in range(w["P"])], dim=1)
+    mp = torch.tensor([0.1, 0.99, 0.99, 0.99])
+
+    def run():
+        t0 = time.perf_counter()
+        O.reference_port_fwd_bwd(A, b, label, graphs, param, mp, seed=7, training=True)
+        return time.perf_counter() - t0
+    return run, B_ref
+
+
+def run_reference_arm(opt, w):
+    """--impl reference: the reference's CPU cost model (oracle port, kind="port"), all host threads, bounded
+    sample per step.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    # size the per-step sample so that (warmup + steps) samples end within ~3 minutes: calibrate on 1 problem
+    cal, _ = cpu_baseline_sample(w, 1)
+    t1 = cal()
+    B_ref = max(1, min(w["B_ref"], int(180.0 / ((opt.steps + opt.warmup) * t1))))
+    run, B_ref = cpu_baseline_sample(w, B_ref)
+    for _ in range(opt.warmup):
+        run()
+    times = [run() for _ in range(opt.steps)]
+    t = sum(times) / len(times)
+    value = w["K"] * B_ref / t
+    sample = f"first {B_ref} problems of {opt.workload} (K={w['K']}), one fwd+bwd per step; cost is linear in batch (Python loops per problem)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
+            "warmup": opt.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "batch_in_sample": B_ref},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(opt, w):
+    import torch.distributed as dist
+    import unfolded_DLASSO
+    import gnn_dlasso_utils
+    from dadmm_b200 import _lib, dist as D
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the D-ADMM hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B_glob = w["B"]
+    lo, hi = D.shard_range(B_glob, rank, world)
+    B_loc = hi - lo
+    args, A, label_h, graphs, param = make_problem(w, B_loc, lo=lo, shared_graph=(opt.workload == "cfg1"))
+    A_dev = A.to(dev)
+    label_dev = label_h.to(dev)
+    b_dev = torch.stack([A_dev[0, p] @ label_dev for p in range(w["P"])], dim=1).contiguous()      # [B,P,m,1]
+    b_host, label_host = b_dev.cpu().pin_memory(), label_h.pin_memory()
+    model = unfolded_DLASSO.DLASSO_unfolded(A_dev, args).to(dev)
+    model.contract_algo = opt.algo
+    with torch.no_grad():
+        model.seq_hyp.param.copy_(param)
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+    def step(b, label):
+        Y, _ = model(b, graphs)
+        loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False, global_batch=B_glob)
+        optim.zero_grad(set_to_none=True)
+        loss_final.backward()
+        if world > 1:
+            D.allreduce_gradients(model)
+        optim.step()
+        return loss_final
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- device-resident timing (value) ------------------------------------------------------------------
+    for _ in range(max(opt.warmup, 3)):
+        step(b_dev, label_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(opt.steps):
+        loss = step(b_dev, label_dev)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) / 1e3) / opt.steps
+    loss_val = float(loss.detach())
+
+    # ---- end to end through the public API with host buffers (e2e) -----------------------------------------
+    def e2e_step():
+        b = b_host.to(dev, non_blocking=True)
+        lab = label_host.to(dev, non_blocking=True)
+        return float(step(b, lab).detach())       # .item(): device->host read of the step's result
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(opt.steps, 5))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    t_e2e = max_over_ranks((time.perf_counter() - t0)) / n_e2e
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (one extra profiled step) -------------------
+    _lib.profile_enable(True)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    step(b_dev, label_dev)
+    p1.record()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    t_prof = p0.elapsed_time(p1)
+    roofline, breakdown = make_roofline(w, B_loc, prof, t_prof)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = w["K"] * B_glob / t_dev
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
+            "ms_per_step": 1e3 * t_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": B_glob,
+                       "batch_per_gpu": B_loc, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "contraction": opt.algo, "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
+                       if B_loc * w["P"] * w["n"] * 4 > 126e6 else "working set fits L2 (small config)",
+                       "step": "forward K iters + compute_loss + loss_final.backward + grad allreduce + Adam"},
+            "clocks": clocks,
+            "e2e": {"value": w["K"] * B_glob / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e,
+                    "h2d_bytes_per_step": (b_host.numel() + label_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "loss_final": loss_val,
+            "roofline": roofline, "kernel_breakdown_ms": breakdown}
+    if opt.cpu_baseline:
+        run, B_ref = cpu_baseline_sample(w)
+        t = min(run() for _ in range(1 if w["P"] >= 50 else 2))
+        line["cpu_baseline"] = {"value": w["K"] * B_ref / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "host_cpus": os.cpu_count(),
+                                "sample": f"first {B_ref} problems of {opt.workload} (K={w['K']}), one fwd+bwd, {t:.1f} s; "
+                                          "cost is linear in batch (Python loops per problem)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def make_roofline(w, B_loc, prof, t_step_ms):
+    """Roofline of the dominant kernel of the step, from the profiled extra step.
+    Contraction (tensor / FMA bound): algorithmic flops per launch = 2*P*n*n*B_loc.
+    Step kernels (HBM bound): algorithmic bytes per iteration*problem = 20*P*n fwd, 36*P*n bwd."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    P, n = w["P"], w["n"]
+    breakdown = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof.items() if v[1]}
+    breakdown["step_total_ms"] = round(t_step_ms, 3)
+    kind = max(("contract_simt", "contract_tc", "step_fwd", "step_bwd"), key=lambda k: prof[k][0])
+    ms, cnt = prof[kind]
+    if kind.startswith("contract"):
+        flops = 2.0 * P * n * n * B_loc
+        ach = flops / (ms / cnt * 1e-3) / 1e12
+        note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). A 3xTF32 "
+                "tcgen05 kernel issues 3 tf32 MMAs at half the bf16 rate, so 1/6 of this peak is its ceiling; "
+                "the SIMT kernel's ceiling is the FP32 FMA pipe (~60-70 TFLOP/s)")
+        roof = {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
+                "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
+                "share_of_step": ms / t_step_ms, "note": note}
+    else:
+        per = (20 if kind == "step_fwd" else 36) * P * n * B_loc
+        ach = per / (ms / cnt * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
+                "share_of_step": ms / t_step_ms}
+    # secondary: HBM fraction of the streaming kernels, always reported
+    for k2, per_elem in (("step_fwd", 20), ("step_bwd", 36)):
+        if prof[k2][1]:
+            m2, c2 = prof[k2]
+            roof[f"{k2}_hbm_frac"] = per_elem * P * n * B_loc / (m2 / c2 * 1e-3) / 1e9 / hbm
+    return roof, breakdown
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    opt = ap.parse_args()
+    w = WORKLOADS[opt.workload]
+    if opt.impl == "reference":
+        run_reference_arm(opt, w)
+    else:
+        run_ours(opt, w)
+
+
+if __name__ == "__main__":
+    main()

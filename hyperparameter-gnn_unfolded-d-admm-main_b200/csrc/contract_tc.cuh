@@ -1,13 +1,371 @@
-// contract_tc.cuh -- tcgen05 (5th-gen tensor core) contraction, fp32-accurate via 3xTF32.
-// Placeholder until the kernel lands: reports every shape as unsupported so AUTO uses SIMT.
+// contract_tc.cuh -- the per-agent contraction out[b,p,:] (+)= W_p x[b,p,:] on the 5th-generation tensor
+// cores (tcgen05 / TMEM / TMA), fp32-accurate through a 3xTF32 split.
+//
+// The reference evaluates `torch.matmul(AtA[0,p], y[:,p])` per agent (unfolded_DLASSO.py:69-71); AtA is
+// shared by the whole batch, so for each agent this is a dense GEMM  D[i,b] = sum_k W_p[i,k] * x[b,p,k]
+// with M = n_out (rows of W_p), N = batch, K = n_in, both operands K-major in global memory.
+//
+// fp32 parity on tf32 tensor cores: every operand value v is used as  v = hi + lo  with hi = the tf32
+// truncation the tensor core applies to the raw fp32 bits and lo = rn_tf32(v - hi); the product is
+// accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  in the fp32 TMEM accumulator (the dropped lo*lo
+// term is <= 2^-20 relative).  The raw fp32 tiles land in shared memory by TMA and double as the "hi"
+// operands; four converter warps derive the "lo" tiles element-wise at the same (swizzled) offsets, so
+// they never have to know the swizzle.
+//
+// Kernel structure (persistent, one CTA per SM, 320 threads):
+//   warp 0      TMA producer      cp.async.bulk.tensor.3d  -> stage ring (4 x {A 128x16, B 256x16} fp32, SW64)
+//   warp 1      MMA issuer        3 x tcgen05.mma.kind::tf32 (M128 N256 K8) per k-step, tcgen05.commit
+//   warps 2-5   lo converters     generic-proxy reads/writes + fence.proxy.async
+//   warps 6-9   epilogue          tcgen05.ld 32x32b.x32 -> coalesced 128-byte row stores (optionally +=)
+//   TMEM: 2 accumulators x 256 columns, so the epilogue of tile t overlaps the main loop of tile t+1.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
-namespace dadmm { namespace tc {
-inline bool dims_supported(int, int, int, int) { return false; }
-inline bool shape_supported(int, int, int, int, const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t,
-                            int64_t, const void*, int64_t, int64_t, int64_t) { return false; }
-inline size_t workspace_bytes(int, int, int, int) { return 0; }
-inline int launch(int, int, int, int, const float*, const float*, float*, int64_t, int64_t, int, void*, size_t, cudaStream_t) {
-    DADMM_FAIL(-4, "tcgen05 contraction not built");
+
+namespace dadmm {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4, ACC = 2;
+constexpr int A_BYTES = BM * BK * 4;             // 8 KB
+constexpr int B_BYTES = BN * BK * 4;             // 16 KB
+constexpr int HALF_BYTES = A_BYTES + B_BYTES;    // raw (= hi) tiles of one stage
+constexpr int STAGE_BYTES = 2 * HALF_BYTES;      // + lo tiles
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 320;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
+constexpr uint32_t TMEM_COLS = 512;
+
+// tcgen05 instruction descriptor: D=f32, A=B=tf32, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-}}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Spin with a watchdog: a protocol bug must surface as a trap, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 27)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 64 bytes,
+// 8-row swizzle atoms 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// lo = rn_tf32(v - trunc_tf32(v)); the tensor core ignores the 13 low mantissa bits of a tf32 operand
+__device__ __forceinline__ float tf32_lo(float v) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    float lo = v - hi;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+    return __uint_as_float(r);
+}
+
+struct Params {
+    int B, P, n_out, n_in;
+    float* out;
+    long long o_sb;   // elements between consecutive problems in `out`
+    int accumulate;
+    int m_tiles, n_tiles, k_blocks, total_tiles;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    // barrier slots (8 bytes each)
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + ACC + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 2 * ACC);
+    auto stage_base = [&](int s) { return base + (uint32_t)s * STAGE_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(conv_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < ACC; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int tiles_per_agent = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
+                const int i0 = (r % p.m_tiles) * BM, b0 = (r / p.m_tiles) * BN;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), HALF_BYTES);
+                    tma_load_3d(stage_base(stage), &map_w, full_bar(stage), kb * BK, i0, ag);
+                    tma_load_3d(stage_base(stage) + A_BYTES, &map_x, full_bar(stage), kb * BK, ag, b0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(conv_bar(stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = stage_base(stage), sb = sa + A_BYTES;
+                    const uint32_t sa_lo = sa + HALF_BYTES, sb_lo = sb + HALF_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t koff = ks * 32;   // 8 tf32 = 32 bytes along K inside the 64-byte swizzled row
+                        const uint64_t da = umma_desc(sa + koff), db = umma_desc(sb + koff);
+                        const uint64_t da_lo = umma_desc(sa_lo + koff), db_lo = umma_desc(sb_lo + koff);
+                        umma_tf32(d_tmem, da_lo, db, (kb | ks) != 0);
+                        umma_tf32(d_tmem, da, db_lo, 1u);
+                        umma_tf32(d_tmem, da, db, 1u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+    } else if (warp < EPI_WARP0) {
+        // ------------------------------------------------------------------ lo converters (128 threads)
+        const int ct = threadIdx.x - CONV_WARP0 * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t src = stage_base(stage), dst = src + HALF_BYTES;
+#pragma unroll 4
+                for (int c = ct; c < HALF_BYTES / 16; c += 128) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * c));
+                    v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                fence_proxy_async();
+                mbar_arrive(conv_bar(stage));
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (128 threads)
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
+            const int i0 = (r % p.m_tiles) * BM, b0 = (r / p.m_tiles) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const int i = i0 + q * 32 + lane;
+            const bool row_ok = i < p.n_out;
+            float* orow = p.out + (long long)ag * p.n_out + i;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int b = b0 + c0 + c;
+                        if (b < p.B) {
+                            float* dst = orow + (long long)b * p.o_sb;
+                            float val = __uint_as_float(v[c]);
+                            if (p.accumulate) val += *dst;
+                            *dst = val;
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+inline bool dims_supported(int B, int P, int n_out, int n_in) {
+    return B >= 128 && n_out >= 64 && n_in >= 16 && (n_in % 4) == 0 && P >= 1;
+}
+
+inline bool shape_supported(int B, int P, int n_out, int n_in, const void* W, int64_t w_sp, int64_t w_si, int64_t w_sk,
+                            const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk, const void* out, int64_t o_sb,
+                            int64_t o_sp, int64_t o_si) {
+    if (!dims_supported(B, P, n_out, n_in)) return false;
+    const bool lay = w_sk == 1 && w_si == n_in && w_sp == (int64_t)n_out * n_in && x_sk == 1 && x_sp == n_in &&
+                     (x_sb % 4) == 0 && x_sb >= (int64_t)P * n_in && o_si == 1 && o_sp == n_out;
+    const bool al = (reinterpret_cast<uintptr_t>(W) % 16 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(out) % 4 == 0);
+    return lay && al && encode_fn() != nullptr;
+}
+
+inline size_t workspace_bytes(int, int, int, int) { return 0; }
+
+inline int launch(int B, int P, int n_out, int n_in, const float* W, const float* x, float* out, int64_t x_sb, int64_t o_sb,
+                  int accumulate, void*, size_t, cudaStream_t s) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
+    CUtensorMap mw, mx;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)n_in, (cuuint64_t)n_out, (cuuint64_t)P};
+        cuuint64_t strides[2] = {(cuuint64_t)n_in * 4, (cuuint64_t)n_out * n_in * 4};
+        cuuint32_t box[3] = {BK, BM, 1}, es[3] = {1, 1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)W, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) DADMM_FAIL(-4, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)n_in, (cuuint64_t)P, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)n_in * 4, (cuuint64_t)x_sb * 4};
+        cuuint32_t box[3] = {BK, 1, BN}, es[3] = {1, 1, 1};
+        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) DADMM_FAIL(-4, "cuTensorMapEncodeTiled(x) failed: %d", (int)r);
+    }
+    Params p;
+    p.B = B; p.P = P; p.n_out = n_out; p.n_in = n_in;
+    p.out = out; p.o_sb = o_sb; p.accumulate = accumulate;
+    p.m_tiles = ceil_div(n_out, BM);
+    p.n_tiles = ceil_div(B, BN);
+    p.k_blocks = ceil_div(n_in, BK);
+    p.total_tiles = P * p.m_tiles * p.n_tiles;
+    static int num_sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    static bool attr_set = false;
+    if (!attr_set) {
+        DADMM_CUDA(cudaFuncSetAttribute(contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = std::min(num_sms, p.total_tiles);
+    ProfScope prof(PROF_CONTRACT_TC, s);
+    contract_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mw, mx, p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace dadmm

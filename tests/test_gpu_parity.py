@@ -293,3 +293,63 @@ def test_properties_at_scale():
     lhs = DF.contract(W, 2 * x1 + x2)
     rhs = 2 * DF.contract(W, x1) + DF.contract(W, x2)
     assert rel_l2(lhs.cpu(), rhs.cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 contraction
+def _tc_available(B, P, n):
+    from dadmm_b200 import _lib
+    return bool(_lib.lib.dadmm_contract_uses_tensor_cores(0, 2, B, P, n, n))
+
+
+@pytest.mark.parametrize("B,P,n", [(256, 2, 128), (300, 3, 500), (1024, 5, 256), (130, 1, 64)])
+def test_contract_tc_3xtf32_vs_fp64(B, P, n):
+    """tcgen05 3xTF32 contraction: fp32-grade accuracy (same order as the FP32-FMA kernel), incl. ragged
+    M/N/K tiles (n=500, B=300) and the accumulate epilogue."""
+    DF, _ = _df()
+    assert _tc_available(B, P, n)
+    gen = torch.Generator().manual_seed(B + n)
+    W = torch.randn((P, n, n), generator=gen)
+    x = torch.randn((B, P, n), generator=gen)
+    ref = torch.einsum("pik,bpk->bpi", W.double(), x.double())
+    Wd, xd = W.to(DEV), x.to(DEV)
+    o_tc = DF.contract(Wd, xd, algo="tc")
+    o_simt = DF.contract(Wd, xd, algo="simt")
+    e_tc, e_simt = rel_l2(o_tc.cpu(), ref), rel_l2(o_simt.cpu(), ref)
+    print(f"contract B={B} P={P} n={n}: rel-L2 vs fp64  tc={e_tc:.2e}  simt={e_simt:.2e}")
+    assert e_tc < 2e-6, (e_tc, e_simt)
+    acc = DF.contract(Wd, xd, out=o_tc.clone(), accumulate=True, algo="tc")
+    assert rel_l2(acc.cpu(), 2 * ref) < 2e-6
+    assert torch.equal(DF.contract(Wd, xd, algo="tc"), o_tc)      # deterministic
+
+
+@pytest.mark.parametrize("a_scale", [0.1, 1.0])
+def test_unfolded_tc_vs_simt_vs_fp64_oracle(a_scale):
+    """K-step trajectories with the tcgen05 contraction against the fp64 oracle, next to the exact-FMA path:
+    the tensor-core path must stay within max(1e-5, 2x) of the FMA path's own distance to fp64."""
+    DF, BG = _df()
+    P, n, m, K, B = 4, 128, 32, 8, 256
+    pr = random_problem(P, n, m, B, K, seed=21, a_scale=a_scale)
+    hyp = O.hyp_table(pr["param"], torch.tensor([0.1, 0.99, 0.99, 0.99]), True)
+    A64 = pr["A"].double()
+    Y64 = O.unfolded_forward(O.atx(A64, A64), O.atx(A64, pr["b"].double()), pr["graphs"], pr["y0"].double(),
+                             pr["U0"].double(), pr["d0"].double(), hyp.double())
+    A = pr["A"].to(DEV)
+    W = DF.atx(A, A)[0].contiguous()
+    Wt = W.transpose(1, 2).contiguous()
+    Atb = DF.atx(A, pr["b"].to(DEV)).squeeze(-1)
+    graph = BG.from_graph_list(pr["graphs"], P, DEV)
+    clamps = [DF.clamps_model1(k) for k in range(K)]
+    outs = {}
+    for algo in ("simt", "tc"):
+        h = hyp.to(DEV).requires_grad_(True)
+        Y = DF.Unfolded.apply(h, W, Wt, Atb, _dev(pr["y0"]), _dev(pr["U0"]), _dev(pr["d0"]), graph, clamps, algo, None, None)
+        losses = DF.MSELoss.apply(Y, pr["label"].to(DEV), None, None)
+        losses[-1].backward()
+        outs[algo] = (Y.detach().cpu(), h.grad.cpu())
+    for k in range(K):
+        e_s, e_t = rel_l2(outs["simt"][0][k], Y64[k]), rel_l2(outs["tc"][0][k], Y64[k])
+        assert e_t <= max(1e-5, 2 * e_s), (k, e_t, e_s)
+    g_s, g_t = outs["simt"][1], outs["tc"][1]
+    print(f"a_scale={a_scale}: Y[K-1] rel-L2 vs fp64: simt={rel_l2(outs['simt'][0][-1], Y64[-1]):.2e} "
+          f"tc={rel_l2(outs['tc'][0][-1], Y64[-1]):.2e}; grad tc vs simt={rel_l2(g_t, g_s):.2e}")
+    assert rel_l2(g_t, g_s) < max(1e-4, 50 * rel_l2(outs["tc"][0][-1], outs["simt"][0][-1]))
