@@ -12,12 +12,18 @@
 // operands; four converter warps derive the "lo" tiles element-wise at the same (swizzled) offsets, so
 // they never have to know the swizzle.
 //
-// Kernel structure (persistent, one CTA per SM, 320 threads):
-//   warp 0      TMA producer      cp.async.bulk.tensor.3d  -> stage ring (4 x {A 128x16, B 256x16} fp32, SW64)
-//   warp 1      MMA issuer        3 x tcgen05.mma.kind::tf32 (M128 N256 K8) per k-step, tcgen05.commit
-//   warps 2-5   lo converters     generic-proxy reads/writes + fence.proxy.async
-//   warps 6-9   epilogue          tcgen05.ld 32x32b.x32 -> coalesced 128-byte row stores (optionally +=)
-//   TMEM: 2 accumulators x 256 columns, so the epilogue of tile t overlaps the main loop of tile t+1.
+// Accumulation: the tcgen05 accumulator TRUNCATES (round-toward-zero) on every accumulate -- measured on
+// B200: a bias of -2^-24 per k-step, i.e. -7e-6 relative at K=1024 (profiles/r01_tc_accumulation_probe.txt),
+// 10x the error of an fp32 FMA loop.  So the tensor core only ever sums K_CHUNK = 64 consecutive k (24 MMAs)
+// from zero into a TMEM buffer; the epilogue warps drain each chunk and add it to fp32 REGISTER accumulators
+// with round-to-nearest.  That restores FMA-loop accuracy and costs no tensor time (two TMEM buffers ping-pong).
+//
+// Kernel structure (persistent, one CTA per SM, 512 threads = 4 warpgroups, setmaxnreg-rebalanced):
+//   warp 0       TMA producer      cp.async.bulk.tensor.3d  -> stage ring (4 x {A 128x16, B 256x16} fp32, SW64)
+//   warp 1       MMA issuer        3 x tcgen05.mma.kind::tf32 (M128 N256 K8) per k-step, tcgen05.commit
+//   warps 4-7    lo converters     generic-proxy reads/writes + fence.proxy.async
+//   warps 8-15   accumulate+store  tcgen05.ld 32x32b.x32 per chunk -> registers (128 per thread); at the end of
+//                                  a tile coalesced 128-byte row stores (optionally +=)
 #pragma once
 #include <cuda.h>
 
@@ -32,8 +38,11 @@ constexpr int B_BYTES = BN * BK * 4;             // 16 KB
 constexpr int HALF_BYTES = A_BYTES + B_BYTES;    // raw (= hi) tiles of one stage
 constexpr int STAGE_BYTES = 2 * HALF_BYTES;      // + lo tiles
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 320;
-constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
+constexpr int NUM_THREADS = 512;
+constexpr int CONV_WARP0 = 4, EPI_WARP0 = 8;
+constexpr int KB_PER_CHUNK = 4;                  // 4 k-blocks of 16 = 64 k per tensor-core partial sum
+constexpr int EPI_THREADS = 256;
+constexpr int COLS_PER_THREAD = BN / 2;          // each accumulate warp owns one lane quarter x one column half
 constexpr uint32_t TMEM_COLS = 512;
 
 // tcgen05 instruction descriptor: D=f32, A=B=tf32, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
@@ -110,6 +119,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // lo = rn_tf32(v - trunc_tf32(v)); the tensor core ignores the 13 low mantissa bits of a tf32 operand
 __device__ __forceinline__ float tf32_lo(float v) {
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -151,7 +165,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         }
         for (int a = 0; a < ACC; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -167,9 +181,12 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
     const int tiles_per_agent = p.m_tiles * p.n_tiles;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+    const int n_chunks = (p.k_blocks + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+
+    if (warp < 4) {
+        reg_dec<40>();
+        if (warp == 0 && lane == 0) {
+            // -------------------------------------------------------------- TMA producer
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
             int stage = 0;
@@ -185,41 +202,42 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // -------------------------------------------------------------- MMA issuer
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(conv_bar(stage), phase);
+            int ci = 0;                                   // running chunk index of this CTA
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait(tempty_bar(buf), ((uint32_t)(ci >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
-                    const uint32_t sa = stage_base(stage), sb = sa + A_BYTES;
-                    const uint32_t sa_lo = sa + HALF_BYTES, sb_lo = sb + HALF_BYTES;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+                    const int kb_end = min(p.k_blocks, (ch + 1) * KB_PER_CHUNK);
+                    for (int kb = ch * KB_PER_CHUNK; kb < kb_end; ++kb) {
+                        mbar_wait(conv_bar(stage), phase);
+                        tcgen05_fence_after();
+                        const uint32_t sa = stage_base(stage), sb = sa + A_BYTES;
+                        const uint32_t sa_lo = sa + HALF_BYTES, sb_lo = sb + HALF_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint32_t koff = ks * 32;   // 8 tf32 = 32 bytes along K inside the 64-byte swizzled row
-                        const uint64_t da = umma_desc(sa + koff), db = umma_desc(sb + koff);
-                        const uint64_t da_lo = umma_desc(sa_lo + koff), db_lo = umma_desc(sb_lo + koff);
-                        umma_tf32(d_tmem, da_lo, db, (kb | ks) != 0);
-                        umma_tf32(d_tmem, da, db_lo, 1u);
-                        umma_tf32(d_tmem, da, db, 1u);
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint32_t koff = ks * 32;   // 8 tf32 = 32 bytes along K inside the 64-byte swizzled row
+                            const uint64_t da = umma_desc(sa + koff), db = umma_desc(sb + koff);
+                            const uint64_t da_lo = umma_desc(sa_lo + koff), db_lo = umma_desc(sb_lo + koff);
+                            umma_tf32(d_tmem, da_lo, db, (kb != ch * KB_PER_CHUNK) || ks != 0);
+                            umma_tf32(d_tmem, da, db_lo, 1u);
+                            umma_tf32(d_tmem, da, db, 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(empty_bar(stage));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    umma_commit(tfull_bar(buf));
                 }
-                umma_commit(tfull_bar(acc));
             }
         }
     } else if (warp < EPI_WARP0) {
         // ------------------------------------------------------------------ lo converters (128 threads)
+        reg_dec<56>();
         const int ct = threadIdx.x - CONV_WARP0 * 32;
         int stage = 0;
         uint32_t phase = 0;
@@ -240,39 +258,50 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (128 threads)
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        // ------------------------------------------------------------------ accumulate + store (256 threads)
+        reg_inc<208>();
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int h = (warp - EPI_WARP0) >> 2;         // column half
+        int ci = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
-            const int i0 = (r % p.m_tiles) * BM, b0 = (r / p.m_tiles) * BN;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tcgen05_fence_after();
-            const int i = i0 + q * 32 + lane;
-            const bool row_ok = i < p.n_out;
-            float* orow = p.out + (long long)ag * p.n_out + i;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                tmem_ld_wait();
-                if (row_ok) {
+            const int i0 = (r % p.m_tiles) * BM, b0 = (r / p.m_tiles) * BN + h * COLS_PER_THREAD;
+            float acc[COLS_PER_THREAD];
+            for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait(tfull_bar(buf), (uint32_t)(ci >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * COLS_PER_THREAD);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int b = b0 + c0 + c;
-                        if (b < p.B) {
-                            float* dst = orow + (long long)b * p.o_sb;
-                            float val = __uint_as_float(v[c]);
-                            if (p.accumulate) val += *dst;
-                            *dst = val;
-                        }
+                for (int j = 0; j < COLS_PER_THREAD / 32; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32u * j, v);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[32 * j + c] = __uint_as_float(v[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[32 * j + c] += __uint_as_float(v[c]);
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(tempty_bar(buf));
+            }
+            const int i = i0 + q * 32 + lane;
+            if (i < p.n_out) {
+                float* orow = p.out + (long long)ag * p.n_out + i;
+#pragma unroll
+                for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                    const int b = b0 + c;
+                    if (b < p.B) {
+                        float* dst = orow + (long long)b * p.o_sb;
+                        float val = acc[c];
+                        if (p.accumulate) val += *dst;
+                        *dst = val;
                     }
                 }
             }
-            tcgen05_fence_before();
-            mbar_arrive(tempty_bar(acc));
         }
     }
 
