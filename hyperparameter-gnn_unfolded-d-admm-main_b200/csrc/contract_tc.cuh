@@ -267,17 +267,29 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
             const int i0 = (r % p.m_tiles) * BM, b0 = (r / p.m_tiles) * BN + h * COLS_PER_THREAD;
             float acc[COLS_PER_THREAD];
+            const int i = i0 + q * 32 + lane;
+            float* orow = p.out + (long long)ag * p.n_out + i;
+            if (p.accumulate) {
+                // out += W x: seed the register accumulators with the old values; the loads fly while the
+                // tensor core works on the first chunk
+#pragma unroll
+                for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                    const int b = b0 + c;
+                    acc[c] = (i < p.n_out && b < p.B) ? __ldcs(orow + (long long)b * p.o_sb) : 0.0f;
+                }
+            }
             for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
                 const int buf = ci & 1;
                 mbar_wait(tfull_bar(buf), (uint32_t)(ci >> 1) & 1u);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * COLS_PER_THREAD);
+                const bool seed = (ch == 0) && !p.accumulate;
 #pragma unroll
                 for (int j = 0; j < COLS_PER_THREAD / 32; ++j) {
                     uint32_t v[32];
                     tmem_ld32(taddr + 32u * j, v);
                     tmem_ld_wait();
-                    if (ch == 0) {
+                    if (seed) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) acc[32 * j + c] = __uint_as_float(v[c]);
                     } else {
@@ -288,18 +300,11 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 tcgen05_fence_before();
                 mbar_arrive(tempty_bar(buf));
             }
-            const int i = i0 + q * 32 + lane;
             if (i < p.n_out) {
-                float* orow = p.out + (long long)ag * p.n_out + i;
 #pragma unroll
                 for (int c = 0; c < COLS_PER_THREAD; ++c) {
                     const int b = b0 + c;
-                    if (b < p.B) {
-                        float* dst = orow + (long long)b * p.o_sb;
-                        float val = acc[c];
-                        if (p.accumulate) val += *dst;
-                        *dst = val;
-                    }
+                    if (b < p.B) orow[(long long)b * p.o_sb] = acc[c];
                 }
             }
         }

@@ -440,18 +440,20 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
     if (K <= 0 || B <= 0 || P <= 0 || n <= 0 || B_norm <= 0) DADMM_FAIL(-1, "loss_fwd: bad dims");
     if (!Y || !label || !losses || !ws) DADMM_FAIL(-1, "loss_fwd: null pointer");
     if (ws_bytes < dadmm_loss_ws_bytes(dtype, K, B, P, n)) DADMM_FAIL(-1, "loss_fwd: workspace too small");
-    const long long per_k = (long long)B * P * n;
-    const int nblk = (int)std::min<long long>(1024, ceil_div64(per_k, 256 * 4));
+    const long long rows = (long long)B * P;
+    const int nblk = (int)std::min<long long>(1024, ceil_div64(rows, 8));
     const double inv = 1.0 / ((double)P * (double)B_norm * (double)n);
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope prof(PROF_LOSS, s);
+    const bool v4 = (n % 4 == 0) && aligned_to(Y, 16) && aligned_to(label, 16);
     if (dtype == DADMM_F32) {
-        loss_partial_kernel<float><<<dim3(nblk, K), 256, 0, s>>>((const float*)Y, (const float*)label, B, P, n, (double*)ws);
+        if (v4) loss_partial_kernel<float, 4><<<dim3(nblk, K), 256, 0, s>>>((const float*)Y, (const float*)label, B, P, n, (double*)ws);
+        else loss_partial_kernel<float, 1><<<dim3(nblk, K), 256, 0, s>>>((const float*)Y, (const float*)label, B, P, n, (double*)ws);
         DADMM_LAUNCHED();
         loss_final_kernel<float><<<K, 256, 0, s>>>((const double*)ws, nblk, K, inv, (float*)losses);
         DADMM_LAUNCHED();
     } else if (dtype == DADMM_F64) {
-        loss_partial_kernel<double><<<dim3(nblk, K), 256, 0, s>>>((const double*)Y, (const double*)label, B, P, n, (double*)ws);
+        loss_partial_kernel<double, 1><<<dim3(nblk, K), 256, 0, s>>>((const double*)Y, (const double*)label, B, P, n, (double*)ws);
         DADMM_LAUNCHED();
         loss_final_kernel<double><<<K, 256, 0, s>>>((const double*)ws, nblk, K, inv, (double*)losses);
         DADMM_LAUNCHED();

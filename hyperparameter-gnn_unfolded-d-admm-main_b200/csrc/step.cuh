@@ -405,30 +405,39 @@ __global__ void __launch_bounds__(256) reduce_hyp_sample_kernel(const T* __restr
 // ---------------------------------------------------------------------------------------------
 // MSE loss per iteration (gnn_dlasso_utils.py:54-66) and its gradient.
 // ---------------------------------------------------------------------------------------------
-// grid = (nblk, K); each CTA sums (Y[k] - label)^2 over a grid-stride range in fp64.
-template <typename T>
+// grid = (nblk, K); one warp per (problem, agent) row, VEC-wide coalesced loads; fp32 within a row segment,
+// fp64 across rows.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) loss_partial_kernel(const T* __restrict__ Y, const T* __restrict__ label,
                                                            int B, int P, int n, double* __restrict__ partial) {
     const int k = blockIdx.y;
-    const long long per_k = (long long)B * P * n;
-    const T* Yk = Y + (long long)k * per_k;
+    const long long rows = (long long)B * P;
+    const T* Yk = Y + (long long)k * rows * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     double acc = 0;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_k; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / n;             // (b,p)
-        const int ii = (int)(e - row * n);
-        const long long b = row / P;
-        const T d = Yk[e] - label[b * n + ii];
-        acc += (double)d * (double)d;
+    for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+        const T* yr = Yk + r * n;
+        const T* lr = label + (r / P) * n;
+        T s = (T)0;
+        for (int i = lane * VEC; i < n; i += 32 * VEC) {
+            const Vec<T, VEC> a = ld_stream<T, VEC>(yr + i);
+            const Vec<T, VEC> l = ld_vec<T, VEC>(lr + i);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const T d = a.v[v] - l.v[v];
+                s += d * d;
+            }
+        }
+        acc += (double)s;
     }
     __shared__ double sh[8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     acc = warp_sum(acc);
     if (lane == 0) sh[warp] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
-        partial[(long long)k * gridDim.x + blockIdx.x] = s;
+        double t = 0;
+        for (int w = 0; w < nw; ++w) t += sh[w];
+        partial[(long long)k * gridDim.x + blockIdx.x] = t;
     }
 }
 
