@@ -12,6 +12,7 @@
 #include "contract_simt.cuh"
 #include "contract_tc.cuh"
 #include "step.cuh"
+#include "unfolded.cuh"
 
 namespace dadmm {
 thread_local char g_err[512] = "";
@@ -99,7 +100,7 @@ static int allow_smem(K kernel, size_t bytes) {
 }
 
 static int check_graph(const dadmm_graph* g, int P) {
-    if (!g || !g->ev_ptr || !g->ev_idx || !g->deg) DADMM_FAIL(-3, "graph: null CSR pointers");
+    if (!g || !g->ev_ptr || !g->ev_idx || !g->deg || !g->adj_ptr || !g->adj_idx) DADMM_FAIL(-3, "graph: null CSR pointers");
     if (g->P != P) DADMM_FAIL(-3, "graph: P mismatch (%d vs %d)", g->P, P);
     if (g->n_graphs < 1) DADMM_FAIL(-3, "graph: n_graphs < 1");
     return 0;
@@ -231,6 +232,196 @@ static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in,
     DADMM_FAIL(-1, "contract: unknown dtype %d", dtype);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// level kernels of the fused K-iteration path (unfolded.cuh)
+// ------------------------------------------------------------------------------------------
+// Tile configuration of a level kernel: `narr` [R][CH] tiles plus (when it fits) the staged neighbour lists of
+// the tile's TB problems.  *list_cap == 0 means "lists stay in global memory".
+static int level_cfg(int dtype, int B, int P, int n, int narr, int max_list, StepCfg* c, size_t* smem, int* list_cap) {
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), c)) return e;     // same vec/TB/nchunks as step_bwd
+    const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es;
+    const size_t lists = (size_t)c->TB * ((size_t)P + 1 + (size_t)std::max(max_list, 1)) * 4;
+    if (narr > 0 && tiles + lists <= 110 * 1024) {
+        *list_cap = std::max(max_list, 1);
+        *smem = tiles + lists;
+    } else {
+        *list_cap = 0;
+        *smem = tiles;
+    }
+    return 0;
+}
+
+template <typename T>
+static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
+                          const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, const void* y,
+                          const void* U_in, const void* d0, const void* a, const void* atb, void* y_next, void* U_out,
+                          void* graw, int32_t* flags, cudaStream_t s) {
+    LevelFwdParams<T> p;
+    p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr);
+    p.lst_ptr = g->ev_ptr; p.lst_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
+    p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
+    p.G = (T)cl_k->G; p.V = (T)cl_k->V;
+    p.hasD = std::isfinite(cl_k->D) ? 1 : 0;
+    p.D = p.hasD ? (T)cl_k->D : std::numeric_limits<T>::infinity();
+    p.Uc_prev = cl_prev ? (T)cl_prev->Uc : (T)0;
+    p.y = (const T*)y; p.U_in = (const T*)U_in; p.d0 = (const T*)d0; p.a = (const T*)a; p.atb = (const T*)atb;
+    p.y_next = (T*)y_next; p.U_out = (T*)U_out; p.graw = (T*)graw; p.flags = flags;
+    StepCfg c;
+    size_t smem = 0;
+    if (int e = level_cfg(dtype, B, P, n, p.first ? 0 : 1, g->max_events, &c, &smem, &p.list_cap)) return e;
+    if (int e = check_aligned(dtype, c.vec, {y, U_in, d0, a, atb, y_next, U_out, graw})) return e;
+    p.TB = c.TB;
+    ProfScope prof(PROF_STEP_FWD, s);
+#define DADMM_LAUNCH_LFWD(VEC)                                                                  \
+    {                                                                                           \
+        if (int e = allow_smem(level_fwd_kernel<T, VEC>, smem)) return e;                       \
+        level_fwd_kernel<T, VEC><<<c.grid, kStepThreads, smem, s>>>(p);                         \
+    }
+    bool launched = false;
+    if constexpr (sizeof(T) == 4) {
+        if (c.vec == 4) {
+            DADMM_LAUNCH_LFWD(4)
+            launched = true;
+        }
+    }
+    if (!launched) {
+        if (c.vec == 2) DADMM_LAUNCH_LFWD(2)
+        else DADMM_LAUNCH_LFWD(1)
+    }
+#undef DADMM_LAUNCH_LFWD
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+template <typename T>
+static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
+                          const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, int top, const void* y,
+                          const void* U_prev, const void* d0, const void* graw, void* Tb, void* C, void* ga,
+                          const void* gY_prev, const void* label, double coef_prev, void* partials, cudaStream_t s) {
+    LevelBwdParams<T> p;
+    p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr); p.top = top;
+    p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx; p.deg = g->deg; p.gid = g->graph_id;
+    p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
+    p.G = (T)cl_k->G; p.V = (T)cl_k->V;
+    p.hasD = std::isfinite(cl_k->D) ? 1 : 0;
+    p.D = p.hasD ? (T)cl_k->D : std::numeric_limits<T>::infinity();
+    p.Uc_prev = cl_prev ? (T)cl_prev->Uc : (T)0;
+    p.y = (const T*)y; p.U_prev = (const T*)U_prev; p.d0 = (const T*)d0; p.graw = (const T*)graw;
+    p.Tb = (T*)Tb; p.C = (T*)C; p.ga = (T*)ga;
+    p.gY_prev = (const T*)gY_prev;
+    p.label = (coef_prev != 0.0) ? (const T*)label : nullptr;
+    p.coef_prev = (T)coef_prev;
+    p.partials = (T*)partials;
+    StepCfg c;
+    size_t smem = 0;
+    if (int e = level_cfg(dtype, B, P, n, 2, g->max_adj, &c, &smem, &p.list_cap)) return e;
+    if (int e = check_aligned(dtype, c.vec, {y, U_prev, d0, graw, Tb, C, ga, gY_prev, label})) return e;
+    p.TB = c.TB;
+    ProfScope prof(PROF_STEP_BWD, s);
+#define DADMM_LAUNCH_LBWD(VEC)                                                                  \
+    {                                                                                           \
+        if (int e = allow_smem(level_bwd_kernel<T, VEC>, smem)) return e;                       \
+        level_bwd_kernel<T, VEC><<<c.grid, kStepThreads, smem, s>>>(p);                         \
+    }
+    bool launched = false;
+    if constexpr (sizeof(T) == 4) {
+        if (c.vec == 4) {
+            DADMM_LAUNCH_LBWD(4)
+            launched = true;
+        }
+    }
+    if (!launched) {
+        if (c.vec == 2) DADMM_LAUNCH_LBWD(2)
+        else DADMM_LAUNCH_LBWD(1)
+    }
+#undef DADMM_LAUNCH_LBWD
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+template <typename T>
+static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                             const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb, const void* y0,
+                             const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, int32_t* flags,
+                             cudaStream_t s) {
+    const size_t es = sizeof(T);
+    const size_t N = (size_t)B * P * n, NB = N * es;
+    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
+    char* w8 = (char*)ws;
+    char* a = w8 + cw;
+    char* pp[2] = {a + NBa, a + 2 * NBa};
+    const int64_t sn = n, sPn = (int64_t)P * n;
+    const size_t row = (size_t)P * 4 * es;
+    for (int k = 0; k < K; ++k) {
+        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
+        // U_j for j >= 1 lives in U_save[j-1] (training) or in a ping-pong buffer (inference)
+        auto Uslot = [&](int j) -> char* { return U_save ? (char*)U_save + (size_t)(j - 1) * NB : pp[j & 1]; };
+        const char* Uin = (k <= 1) ? (const char*)U0 : Uslot(k - 1);
+        char* Uout = (k == 0 || k == K - 1) ? nullptr : Uslot(k);   // U_{K-1} is consumed in-register only
+        if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, w8, cw, s))
+            return e;
+        if (int e = level_fwd_impl<T>(dtype, B, P, n, graph, clamps + k, k ? clamps + k - 1 : nullptr, (const char*)hyp + k * row,
+                                      k ? (const char*)hyp + (k - 1) * row : nullptr, yk, Uin, d0, a, Atb,
+                                      (char*)Y + (size_t)k * NB, Uout, R_save ? (char*)R_save + (size_t)k * NB : nullptr,
+                                      flags ? flags + k : nullptr, s))
+            return e;
+    }
+    return 0;
+}
+
+template <typename T>
+static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
+                             const dadmm_clamps* clamps, const void* hyp, const void* Wt, const void* y0, const void* U0,
+                             const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
+                             const void* label, const double* loss_coef, void* ghyp, void* ws, cudaStream_t s) {
+    const size_t es = sizeof(T);
+    const size_t N = (size_t)B * P * n, NB = N * es;
+    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
+    char* w8 = (char*)ws;
+    char *Tb = w8 + cw, *C = Tb + NBa, *ga = C + NBa, *part = ga + NBa;
+    const int64_t sn = n, sPn = (int64_t)P * n;
+    const size_t row = (size_t)P * 4 * es;
+    const bool fused = label && loss_coef;
+    DADMM_CUDA(cudaMemsetAsync(ghyp, 0, (size_t)K * row, s));
+    {   // adjoint of y_K
+        const long long rows = (long long)B * P;
+        const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
+        ProfScope prof(PROF_LOSS, s);
+        seed_adjoint_kernel<T><<<nblk, 256, 0, s>>>((const T*)((const char*)Y + (size_t)(K - 1) * NB),
+                                                   gY ? (const T*)((const char*)gY + (size_t)(K - 1) * NB) : nullptr,
+                                                   (fused && loss_coef[K - 1] != 0.0) ? (const T*)label : nullptr,
+                                                   (T)(fused ? loss_coef[K - 1] : 0.0), B, P, n, (T*)Tb);
+        DADMM_LAUNCHED();
+    }
+    int nchunks = 0;
+    if (int e = bwd_nchunks(dtype, B, P, n, &nchunks)) return e;
+    for (int k = K - 1; k >= 0; --k) {
+        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
+        const char* Uprev = (k <= 1) ? (const char*)U0 : (const char*)U_save + (size_t)(k - 2) * NB;   // U_{k-1}
+        if (int e = level_bwd_impl<T>(dtype, B, P, n, graph, clamps + k, k ? clamps + k - 1 : nullptr, (const char*)hyp + k * row,
+                                      k ? (const char*)hyp + (k - 1) * row : nullptr, k == K - 1, yk, Uprev, d0,
+                                      (const char*)R_save + (size_t)k * NB, Tb, C, ga,
+                                      (gY && k) ? (const char*)gY + (size_t)(k - 1) * NB : nullptr, label,
+                                      (fused && k) ? loss_coef[k - 1] : 0.0, part, s))
+            return e;
+        {
+            ProfScope prof(PROF_REDUCE_HYP, s);
+            reduce_level_kernel<T><<<P, 256, 0, s>>>((const T*)part, nchunks, B, P, (T*)((char*)ghyp + k * row),
+                                                    k ? (T*)((char*)ghyp + (k - 1) * row) : nullptr);
+            DADMM_LAUNCHED();
+        }
+        if (k > 0) {
+            if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s))
+                return e;
+        }
+    }
+    return 0;
+}
+
 }  // namespace dadmm
 
 using namespace dadmm;
@@ -353,10 +544,10 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
 size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward) {
     (void)K;
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
-    const size_t N = (size_t)B * P * n;
+    const size_t NBa = ((size_t)B * P * n * es + 255) / 256 * 256;
     const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
-    if (!backward) return cw + 3 * N * es;                                // AtAy + two U ping-pong buffers
-    return cw + 4 * N * es + (partials_elems(B, P, n) * es + 255) / 256 * 256;  // gy, ga, gU, gd + partials
+    if (!backward) return cw + 3 * NBa;                                   // AtAy + two U ping-pong buffers
+    return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256;     // T, C, gAtAy + partials
 }
 
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
@@ -367,28 +558,13 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
     if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0)) DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
-    const size_t es = dtype == DADMM_F64 ? 8 : 4;
-    const size_t N = (size_t)B * P * n, NB = N * es;
-    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
-    char* w8 = (char*)ws;
-    void* cws = w8;
-    char* a = w8 + cw;
-    char* pp[2] = {a + NB, a + 2 * NB};
-    const int64_t sn = n, sPn = (int64_t)P * n;
-    for (int k = 0; k < K; ++k) {
-        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
-        const char* Uk = k ? (U_save ? (const char*)U_save + (size_t)(k - 1) * NB : pp[(k - 1) & 1]) : (const char*)U0;
-        char* Un = (k == K - 1) ? nullptr : (U_save ? (char*)U_save + (size_t)k * NB : pp[k & 1]);
-        if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, cws,
-                                  cw, (cudaStream_t)stream))
-            return e;
-        dadmm_hyp h{(const char*)hyp + (size_t)k * P * 4 * es, 0, 4, 1};
-        if (int e = dadmm_step_fwd(dtype, B, P, n, graph, clamps + k, &h, yk, Uk, k ? nullptr : d0, a, Atb,
-                                   (char*)Y + (size_t)k * NB, Un, nullptr, R_save ? (char*)R_save + (size_t)k * NB : nullptr,
-                                   flags ? flags + k : nullptr, stream))
-            return e;
-    }
-    return 0;
+    if (dtype == DADMM_F32)
+        return unfolded_fwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
+                                        (cudaStream_t)stream);
+    if (dtype == DADMM_F64)
+        return unfolded_fwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
+                                         (cudaStream_t)stream);
+    DADMM_FAIL(-1, "unfolded_fwd: unknown dtype %d", dtype);
 }
 
 int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
@@ -398,36 +574,16 @@ int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const da
                        dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_bwd: bad dims");
     if (!clamps || !hyp || !Wt || !y0 || !U0 || !d0 || !Y || !R_save || !ghyp || !ws) DADMM_FAIL(-1, "unfolded_bwd: null pointer");
-    if (K > 1 && !U_save) DADMM_FAIL(-1, "unfolded_bwd: U_save required");
+    if (K > 2 && !U_save) DADMM_FAIL(-1, "unfolded_bwd: U_save required");
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 1)) DADMM_FAIL(-1, "unfolded_bwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
-    const size_t es = dtype == DADMM_F64 ? 8 : 4;
-    const size_t N = (size_t)B * P * n, NB = N * es;
-    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
-    char* w8 = (char*)ws;
-    void* cws = w8;
-    char *gy = w8 + cw, *ga = gy + NB, *gU = ga + NB, *gd = gU + NB, *part = gd + NB;
-    const int64_t sn = n, sPn = (int64_t)P * n;
-    for (int k = K - 1; k >= 0; --k) {
-        const bool first = (k == K - 1);
-        const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
-        const char* Uk = k ? (const char*)U_save + (size_t)(k - 1) * NB : (const char*)U0;
-        dadmm_hyp h{(const char*)hyp + (size_t)k * P * 4 * es, 0, 4, 1};
-        const double coef = (label && loss_coef) ? loss_coef[k] : 0.0;
-        if (int e = dadmm_step_bwd(dtype, B, P, n, graph, clamps + k, &h, yk, Uk, k ? nullptr : d0,
-                                   (const char*)R_save + (size_t)k * NB, (const char*)Y + (size_t)k * NB,
-                                   first ? nullptr : gy, gY ? (const char*)gY + (size_t)k * NB : nullptr,
-                                   first ? nullptr : gU, first ? nullptr : gd, label, coef, gy, ga, gU, gd, part, stream))
-            return e;
-        if (int e = dadmm_reduce_hyp(dtype, B, P, n, part, 0, (char*)ghyp + (size_t)k * P * 4 * es, 0, 4, 1, 0, stream))
-            return e;
-        if (k > 0) {
-            if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, gy, sPn, sn, 1, 1,
-                                      cws, cw, (cudaStream_t)stream))
-                return e;
-        }
-    }
-    return 0;
+    if (dtype == DADMM_F32)
+        return unfolded_bwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, y0, U0, d0, Y, U_save, R_save, gY, label,
+                                        loss_coef, ghyp, ws, (cudaStream_t)stream);
+    if (dtype == DADMM_F64)
+        return unfolded_bwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, y0, U0, d0, Y, U_save, R_save, gY, label,
+                                         loss_coef, ghyp, ws, (cudaStream_t)stream);
+    DADMM_FAIL(-1, "unfolded_bwd: unknown dtype %d", dtype);
 }
 
 size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n) {

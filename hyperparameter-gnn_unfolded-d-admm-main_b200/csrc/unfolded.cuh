@@ -1,0 +1,413 @@
+// unfolded.cuh -- "level" kernels of the fused K-iteration path (model #1: hyper-parameters shared by the
+// batch).  Same tile decomposition as step.cuh (CTA = TB problems x all P agents x 32*VEC unknowns, one warp
+// per (problem, agent) row segment), but the recurrence is re-associated so that each launch needs ONE
+// shared-memory tile of y_k and every state tensor crosses HBM once:
+//
+//   forward level k   (reads a_k=AtA y_k, Atb, y_k, U_{k-1}; writes y_{k+1}, U_k, r_k)
+//       d_k = k ? clampD(2L y_k) : d_0                 U_k = k ? clamp(U_{k-1} + d_k*eta_{k-1}, Uc_{k-1}) : U_0
+//       r_k = a_k - Atb + sign(y_k) tau_k + U_k deg + d_k rho_k
+//       y_{k+1} = clamp(y_k - alpha_k clamp(r_k, G_k), V_k)
+//     -- the dual update of reference iteration k-1 (unfolded_DLASSO.py:95-99) is evaluated at the start of
+//        level k, where 2L y_k is needed anyway for the gradient (:73-77); values are bit-identical
+//        (2L y_k is accumulated in the reference's event order).
+//
+//   backward level k  (reads T=adj(y_{k+1}), C=adj(U_k), y_k, U_{k-1}, r_k; writes gAtAy_k, S, adj(U_{k-1}))
+//       zb = T 1[|z_k|<=V_k]            rb = -alpha_k zb 1[|r_k|<=G_k]              -> gAtAy_k = rb
+//       Uk = C + deg rb                 Um = Uk 1[|U_{k-1} + d_k eta_{k-1}|<=Uc_{k-1}]  -> adj(U_{k-1}) = Um
+//       db = (rho_k rb + eta_{k-1} Um) 1[|2L y_k|<=D]
+//       S  = zb + gY[k-1] + coef_{k-1}(y_k - label) + 2L db      (the caller adds W^T rb:  adj(y_k) = S + W^T rb)
+//       d alpha_k = -<zb, g_k>, d tau_k = <rb, sign y_k>, d rho_k = <rb, d_k>, d eta_{k-1} = <Um, d_k>
+//     -- here 2L x is evaluated as 2(deg x_q - sum_j x_j) over the plain neighbour list (half the terms of the
+//        event order; the backward pass has no bit pattern to reproduce).
+//
+// These kernels are instruction-issue sensitive (ncu, round 1: the first version executed ~1100 warp
+// instructions per row segment and sat at 22 % of HBM peak), so: the tile's neighbour lists are staged in shared
+// memory once per CTA as pre-scaled row offsets (no shuffles / index arithmetic in the inner loop), rows are
+// walked without integer division, the next row's global loads are issued before the current row's
+// shared-memory work (register double buffering), and the four hyper-parameter partial sums share one
+// 6-shuffle reduction.
+#pragma once
+#include "step.cuh"
+
+namespace dadmm {
+
+template <typename T>
+struct LevelFwdParams {
+    int B, P, n, TB, first, list_cap;   // list_cap: shared-memory ints reserved per problem for its neighbour list
+    const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // event lists (exact order)
+    const T *hyp_k, *hyp_prev;          // rows [P,4] of the table
+    T G, V, D, Uc_prev;
+    int hasD;
+    const T *y, *U_in, *d0, *a, *atb;
+    T *y_next, *U_out, *graw;
+    int32_t* flags;
+};
+
+template <typename T>
+struct LevelBwdParams {
+    int B, P, n, TB, first, top, list_cap;
+    const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // plain adjacency lists
+    const T *hyp_k, *hyp_prev;
+    T G, V, D, Uc_prev;
+    int hasD;
+    const T *y, *U_prev, *d0, *graw;
+    T *Tb, *C, *ga;
+    const T *gY_prev, *label;
+    T coef_prev;
+    T* partials;
+};
+
+// Stage the neighbour lists of the tile's problems: sPtr[bl][0..P] = list bounds relative to sIdx[bl],
+// sIdx[bl][e] = neighbour row ids.  When the lists do not fit
+// (list_cap == 0) the kernels read them from global memory instead.
+template <typename T, int VEC>
+__device__ __forceinline__ void stage_lists(int32_t* sPtr, int32_t* sIdx, int TB, int P, int B, int b0, int cap,
+                                            const int32_t* __restrict__ lst_ptr, const int32_t* __restrict__ lst_idx,
+                                            const int32_t* __restrict__ gid) {
+    for (int bl = 0; bl < TB; ++bl) {
+        const int b = b0 + bl;
+        if (b >= B) break;
+        const int node0 = (gid ? __ldg(gid + b) : 0) * P;
+        const int e0 = __ldg(lst_ptr + node0);
+        for (int q = threadIdx.x; q <= P; q += blockDim.x) sPtr[bl * (P + 1) + q] = __ldg(lst_ptr + node0 + q) - e0;
+        const int cnt = __ldg(lst_ptr + node0 + P) - e0;
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) sIdx[bl * cap + e] = __ldg(lst_idx + e0 + e);
+    }
+}
+
+// 2L x for row q in the reference's event order (sequential (x_q - x_e) accumulation)
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> lap_events(const unsigned char* tile, const Vec<T, VEC>& xq, const int32_t* sIdx,
+                                                  int e0, int e1, int lane_bytes) {
+    Vec<T, VEC> acc = vzero<T, VEC>();
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+        const Vec<T, VEC> xj = *reinterpret_cast<const Vec<T, VEC>*>(tile + sIdx[e] * (32 * VEC * (int)sizeof(T)) + lane_bytes);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc.v[v] = add_rn(acc.v[v], sub_rn(xq.v[v], xj.v[v]));
+    }
+    return acc;
+}
+
+// 2L x = 2 (deg x_q - sum_j x_j) over the plain neighbour list
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> lap_adj(const unsigned char* tile, const Vec<T, VEC>& xq, const int32_t* sIdx,
+                                               int e0, int e1, int lane_bytes) {
+    Vec<T, VEC> acc = vzero<T, VEC>();
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+        const Vec<T, VEC> xj = *reinterpret_cast<const Vec<T, VEC>*>(tile + sIdx[e] * (32 * VEC * (int)sizeof(T)) + lane_bytes);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc.v[v] += xj.v[v];
+    }
+    const T dq = (T)(e1 - e0);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc.v[v] = (T)2 * (dq * xq.v[v] - acc.v[v]);
+    return acc;
+}
+
+// sums of four per-lane values in 6 shuffles; results land in lanes 0 (a), 8 (b), 16 (c), 24 (d)
+template <typename T>
+__device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
+    const bool hi = lane & 16;
+    T k0 = hi ? c : a, k1 = hi ? d : b;
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? a : c, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? b : d, 16);
+    const bool h8 = lane & 8;
+    T k = h8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kStepThreads) level_fwd_kernel(const LevelFwdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CH = 32 * VEC;
+    using V = Vec<T, VEC>;
+    const int P = p.P, R = p.TB * P;
+    unsigned char* S0 = smem_raw;                                              // y_k tile [R][CH]
+    int32_t* sPtr = reinterpret_cast<int32_t*>(S0 + (size_t)R * CH * sizeof(T));
+    int32_t* sIdx = sPtr + p.TB * (P + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int lane_bytes = lane * VEC * (int)sizeof(T);
+    const int nchunks = (p.n + CH - 1) / CH;
+    const int chunk = blockIdx.x % nchunks;
+    const int b0 = (blockIdx.x / nchunks) * p.TB;
+    const int i = chunk * CH + lane * VEC;
+    const bool act_i = i < p.n;
+    const bool first = p.first != 0;
+
+    const bool staged = p.list_cap > 0;
+    if (!first) {
+        if (staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+        for (int bl = 0; bl < p.TB; ++bl) {
+            const int b = b0 + bl;
+            const T* src = p.y + (size_t)b * P * p.n + i;
+            for (int pp = warp; pp < P; pp += nwarps) {
+                V v = vzero<T, VEC>();
+                if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (size_t)pp * p.n);
+                *reinterpret_cast<V*>(S0 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    struct Row { V a, atb, U, y, d; };
+    unsigned bad = 0;
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        if (b >= p.B) break;
+        const size_t base = (size_t)b * P * p.n + i;
+        const int node0 = (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
+        const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
+        auto issue = [&](int pp, Row& L) {
+            L.a = L.atb = L.U = L.y = L.d = vzero<T, VEC>();
+            if (pp < P && act_i) {
+                const size_t off = base + (size_t)pp * p.n;
+                L.a = ld_stream<T, VEC>(p.a + off);
+                L.atb = ld_stream<T, VEC>(p.atb + off);
+                L.U = ld_stream<T, VEC>(p.U_in + off);
+                if (first) {
+                    L.y = ld_vec<T, VEC>(p.y + off);
+                    L.d = ld_stream<T, VEC>(p.d0 + off);
+                }
+            }
+        };
+        Row cur, nxt;
+        issue(warp, cur);
+        for (int pp = warp; pp < P; pp += nwarps) {
+            issue(pp + nwarps, nxt);
+            const size_t off = base + (size_t)pp * p.n;
+            const T alpha = __ldg(p.hyp_k + pp * 4), tau = __ldg(p.hyp_k + pp * 4 + 1), rho = __ldg(p.hyp_k + pp * 4 + 2);
+            const T dg = (T)__ldg(p.deg + node0 + pp);
+            V yv = cur.y, dv = cur.d, Uv = cur.U;
+            if (!first) {
+                yv = *reinterpret_cast<const V*>(tile + (size_t)pp * CH * sizeof(T) + lane_bytes);
+                dv = lap_events<T, VEC>(tile, yv, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
+                const T eta_prev = __ldg(p.hyp_prev + pp * 4 + 3);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (p.hasD) dv.v[v] = clamp_sym(dv.v[v], p.D);
+                    Uv.v[v] = clamp_sym(add_rn(Uv.v[v], mul_rn(dv.v[v], eta_prev)), p.Uc_prev);
+                }
+            }
+            V yn, rv;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const T y = yv.v[v], U = Uv.v[v];
+                T rr = sub_rn(cur.a.v[v], cur.atb.v[v]);
+                rr = add_rn(rr, mul_rn(sign_of(y), tau));
+                rr = add_rn(rr, mul_rn(U, dg));
+                rr = add_rn(rr, mul_rn(dv.v[v], rho));
+                const T g = clamp_sym(rr, p.G);
+                const T z = clamp_sym(sub_rn(y, mul_rn(alpha, g)), p.V);
+                rv.v[v] = rr;
+                yn.v[v] = z;
+                // non-finite detection (reference guards): y or U not finite, gradient NaN, y+ not finite
+                bad |= (finite_val(y) ? 0u : 1u) | (finite_val(U) ? 0u : 2u) | ((g != g) ? 4u : 0u) | (finite_val(z) ? 0u : 8u);
+            }
+            if (act_i) {
+                st_vec<T, VEC>(p.y_next + off, yn);
+                if (p.U_out && !first) st_stream<T, VEC>(p.U_out + off, Uv);
+                if (p.graw) st_stream<T, VEC>(p.graw + off, rv);
+            }
+            cur = nxt;
+        }
+    }
+    if (p.flags) {
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        if (bad && lane == 0) atomicOr(p.flags, (int)bad);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kStepThreads) level_bwd_kernel(const LevelBwdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CH = 32 * VEC;
+    using V = Vec<T, VEC>;
+    const int P = p.P, R = p.TB * P;
+    unsigned char* S0 = smem_raw;                                   // y_k tile
+    unsigned char* S1 = S0 + (size_t)R * CH * sizeof(T);            // adjoint of the unclamped 2L y_k
+    int32_t* sPtr = reinterpret_cast<int32_t*>(S1 + (size_t)R * CH * sizeof(T));
+    int32_t* sIdx = sPtr + p.TB * (P + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int lane_bytes = lane * VEC * (int)sizeof(T);
+    const int nchunks = (p.n + CH - 1) / CH;
+    const int chunk = blockIdx.x % nchunks;
+    const int b0 = (blockIdx.x / nchunks) * p.TB;
+    const int i = chunk * CH + lane * VEC;
+    const bool act_i = i < p.n;
+    const bool first = p.first != 0, top = p.top != 0;
+
+    const bool staged = p.list_cap > 0;
+    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        const T* src = p.y + (size_t)b * P * p.n + i;
+        for (int pp = warp; pp < P; pp += nwarps) {
+            V v = vzero<T, VEC>();
+            if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (size_t)pp * p.n);
+            *reinterpret_cast<V*>(S0 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
+            if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
+        }
+    }
+    __syncthreads();
+
+    struct Row { V t, c, r, u, d, g, l; };
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        if (b >= p.B) break;
+        const size_t base = (size_t)b * P * p.n + i;
+        const int node0 = (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
+        unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
+        const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
+        const T* lab = p.label ? p.label + (size_t)b * p.n + i : nullptr;
+        auto issue = [&](int pp, Row& L) {
+            L.t = L.c = L.r = L.u = L.d = L.g = vzero<T, VEC>();
+            if (pp < P && act_i) {
+                const size_t off = base + (size_t)pp * p.n;
+                L.t = ld_vec<T, VEC>(p.Tb + off);
+                L.r = ld_stream<T, VEC>(p.graw + off);
+                if (first) {
+                    L.d = ld_stream<T, VEC>(p.d0 + off);
+                } else {
+                    if (!top) L.c = ld_vec<T, VEC>(p.C + off);
+                    L.u = ld_stream<T, VEC>(p.U_prev + off);
+                    if (p.gY_prev) L.g = ld_stream<T, VEC>(p.gY_prev + off);
+                }
+            }
+        };
+        V labv = vzero<T, VEC>();
+        if (lab && act_i) labv = ld_vec<T, VEC>(lab);
+        Row cur, nxt;
+        issue(warp, cur);
+        for (int pp = warp; pp < P; pp += nwarps) {
+            issue(pp + nwarps, nxt);
+            const size_t off = base + (size_t)pp * p.n;
+            const T alpha = __ldg(p.hyp_k + pp * 4), rho = __ldg(p.hyp_k + pp * 4 + 2);
+            const T dg = (T)__ldg(p.deg + node0 + pp);
+            const V yv = *reinterpret_cast<const V*>(tile + (size_t)pp * CH * sizeof(T) + lane_bytes);
+            V draw = cur.d;
+            T eta_prev = (T)0;
+            if (!first) {
+                draw = lap_adj<T, VEC>(tile, yv, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
+                eta_prev = __ldg(p.hyp_prev + pp * 4 + 3);
+            }
+            V o_ga, o_c, o_dir, o_db;
+            T pa = (T)0, pt = (T)0, pr = (T)0, pe = (T)0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const T y = yv.v[v], rr = cur.r.v[v];
+                const bool mD = (first || !p.hasD) ? true : in_closed(draw.v[v], p.D);
+                const T d = (first || !p.hasD) ? draw.v[v] : clamp_sym(draw.v[v], p.D);
+                const T g = clamp_sym(rr, p.G);
+                const T z = sub_rn(y, mul_rn(alpha, g));
+                const T zb = in_closed(z, p.V) ? cur.t.v[v] : (T)0;
+                pa -= zb * g;
+                const T rb = in_closed(rr, p.G) ? (-alpha * zb) : (T)0;
+                pt += rb * sign_of(y);
+                pr += rb * d;
+                o_ga.v[v] = rb;
+                if (!first) {
+                    const T uk = cur.c.v[v] + dg * rb;
+                    const T w = add_rn(cur.u.v[v], mul_rn(d, eta_prev));
+                    const T um = in_closed(w, p.Uc_prev) ? uk : (T)0;
+                    pe += um * d;
+                    o_c.v[v] = um;
+                    const T db = rho * rb + eta_prev * um;
+                    o_db.v[v] = (mD && act_i) ? db : (T)0;
+                    T dir = zb + cur.g.v[v];
+                    if (lab) dir += p.coef_prev * (y - labv.v[v]);
+                    o_dir.v[v] = dir;
+                }
+            }
+            if (!first) {
+                *reinterpret_cast<V*>(tile1 + (size_t)pp * CH * sizeof(T) + lane_bytes) = o_db;
+                if (act_i) {
+                    st_vec<T, VEC>(p.ga + off, o_ga);
+                    st_vec<T, VEC>(p.C + off, o_c);
+                    st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
+                }
+            }
+            const T s = warp_sum4(pa, pt, pr, pe, lane);
+            if ((lane & 7) == 0) p.partials[(((size_t)chunk * p.B + b) * P + pp) * 4 + (lane >> 3)] = s;
+            cur = nxt;
+        }
+    }
+    if (first) return;
+    __syncthreads();
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        if (b >= p.B) break;
+        const size_t base = (size_t)b * P * p.n + i;
+        const unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
+        const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
+        for (int pp = warp; pp < P; pp += nwarps) {
+            const V xq = *reinterpret_cast<const V*>(tile1 + (size_t)pp * CH * sizeof(T) + lane_bytes);
+            const V lt = lap_adj<T, VEC>(tile1, xq, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
+            if (act_i) {
+                const size_t off = base + (size_t)pp * p.n;
+                V s = ld_vec<T, VEC>(p.Tb + off);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) s.v[v] += lt.v[v];
+                st_vec<T, VEC>(p.Tb + off, s);
+            }
+        }
+    }
+}
+
+// hyper-parameter gradient rows from the level partials [nchunks][B][P][4] = (d alpha_k, d tau_k, d rho_k, d eta_{k-1})
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_level_kernel(const T* __restrict__ part, int nchunks, int B, int P,
+                                                           T* row_k, T* row_prev) {
+    const int pp = blockIdx.x;
+    double acc[4] = {0, 0, 0, 0};
+    const long long rows = (long long)nchunks * B;
+    for (long long rI = threadIdx.x; rI < rows; rI += blockDim.x) {
+        const Vec<T, 4> q = ld_vec<T, 4>(part + (rI * P + pp) * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += (double)q.v[c];
+    }
+    __shared__ double sh[4][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double s = warp_sum(acc[c]);
+        if (lane == 0) sh[c][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+        if (threadIdx.x < 3) row_k[pp * 4 + threadIdx.x] = (T)s;
+        else if (row_prev) row_prev[pp * 4 + 3] = (T)s;
+    }
+}
+
+// T = gY_last + coef * (Y_last - label): adjoint of y_K entering the reverse sweep
+template <typename T>
+__global__ void __launch_bounds__(256) seed_adjoint_kernel(const T* __restrict__ Ylast, const T* __restrict__ gYlast,
+                                                           const T* __restrict__ label, T coef, int B, int P, int n,
+                                                           T* __restrict__ out) {
+    const long long rows = (long long)B * P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+        const long long base = r * n;
+        const T* lr = label ? label + (r / P) * n : nullptr;
+        for (int i = lane; i < n; i += 32) {
+            T v = gYlast ? gYlast[base + i] : (T)0;
+            if (lr) v += coef * (Ylast[base + i] - lr[i]);
+            out[base + i] = v;
+        }
+    }
+}
+
+}  // namespace dadmm

@@ -14,6 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
+ABI_VERSION = 2
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32 = 0, 1, 2
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32}
@@ -22,7 +23,8 @@ FLAG_Y, FLAG_U, FLAG_GRAD, FLAG_YNEXT = 1, 2, 4, 8
 
 class Graph(C.Structure):
     _fields_ = [("n_graphs", C.c_int32), ("P", C.c_int32), ("ev_ptr", C.c_void_p), ("ev_idx", C.c_void_p),
-                ("deg", C.c_void_p), ("graph_id", C.c_void_p)]
+                ("deg", C.c_void_p), ("graph_id", C.c_void_p), ("adj_ptr", C.c_void_p), ("adj_idx", C.c_void_p),
+                ("max_events", C.c_int32), ("max_adj", C.c_int32)]
 
 
 class Clamps(C.Structure):
@@ -73,8 +75,8 @@ def _load():
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.dadmm_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.dadmm_abi_version()} != 1")
+    if lib.dadmm_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.dadmm_abi_version()} != {ABI_VERSION}")
     return lib, tuple(sigs)
 
 

@@ -223,9 +223,9 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
     def compute_sum_neighbors(self, graph_list):
         params = list(self.parameters())
         device = params[0].device if params else torch.device("cpu")
-        _, _, deg, gid, G = BatchGraph.build_host(graph_list, self.P)
-        deg = torch.from_numpy(deg).view(G, self.P)
-        deg = deg[torch.from_numpy(gid).long()] if gid is not None else deg.expand(len(graph_list), self.P)
+        host = BatchGraph.build_host(graph_list, self.P)
+        deg = torch.from_numpy(host.deg).view(host.n_graphs, self.P)
+        deg = deg[torch.from_numpy(host.graph_id).long()] if host.graph_id is not None else deg.expand(len(graph_list), self.P)
         return deg.to(device=device, dtype=torch.float32).reshape(len(graph_list), self.P, 1, 1)
 
     def compute_Atx(self, x):

@@ -147,10 +147,10 @@ class DLASSO_unfolded(nn.Module):
     # ------------------------------------------------------------------ reference helper API
     def compute_sum_neighbors(self, graph_list, device):
         """[B,P,1,1] float degrees (reference :111-118)."""
-        ptr, idx, deg, gid, G = BatchGraph.build_host(graph_list, self.P)
-        deg = torch.from_numpy(deg).view(G, self.P)
-        if gid is not None:
-            deg = deg[torch.from_numpy(gid).long()]
+        host = BatchGraph.build_host(graph_list, self.P)
+        deg = torch.from_numpy(host.deg).view(host.n_graphs, self.P)
+        if host.graph_id is not None:
+            deg = deg[torch.from_numpy(host.graph_id).long()]
         else:
             deg = deg.expand(len(graph_list), self.P)
         return deg.to(device=device, dtype=torch.float32).reshape(len(graph_list), self.P, 1, 1)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 1
+#define DADMM_ABI_VERSION 2
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -64,6 +64,12 @@ typedef struct dadmm_graph {
     const int32_t* ev_idx;   /* device, [ev_ptr[n_graphs*P]]                               */
     const int32_t* deg;      /* device, [n_graphs*P]: len(list(graph.neighbors(p)))        */
     const int32_t* graph_id; /* device, [B], or NULL when every problem uses graph 0       */
+    /* plain neighbour lists (each neighbour once, self-loops dropped): 2L x = 2(|adj| x_q - sum_j x_j); used
+     * where no bit pattern has to be reproduced (backward pass) */
+    const int32_t* adj_ptr;  /* device, [n_graphs*P + 1]                                   */
+    const int32_t* adj_idx;  /* device, [adj_ptr[n_graphs*P]]                              */
+    int32_t max_events;      /* host: largest total event count of one graph (sizes shared-memory staging) */
+    int32_t max_adj;         /* host: largest total neighbour count of one graph           */
 } dadmm_graph;
 
 /* element-wise clamp bounds of one iteration (unfolded_DLASSO.py:80-81,92-93,99;

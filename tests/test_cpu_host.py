@@ -23,7 +23,7 @@ def test_library_loads_and_exports_header_symbols():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/dadmm.h but not exported"
     assert set(_lib.EXPORTED) == declared
-    assert _lib.lib.dadmm_abi_version() == 1
+    assert _lib.lib.dadmm_abi_version() == 2
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu():
@@ -34,6 +34,7 @@ def test_invalid_arguments_return_error_codes_without_a_gpu():
     assert rc < 0 and b"null pointer" in _lib.lib.dadmm_last_error()
     assert _lib.lib.dadmm_partials_elems(0, 4, 5, 100) == 4 * 4 * 5 * 4
     assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 2, 3, 8, 4, 0) >= 3 * 2 * 3 * 8 * 4
+    assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 3, 5, 51, 15, 1) % 256 == 0
 
 
 def test_cpu_tensors_are_rejected_loudly():
@@ -47,7 +48,8 @@ def test_cpu_tensors_are_rejected_loudly():
 def test_event_csr_matches_oracle(name):
     from dadmm_b200.graph import BatchGraph
     g = Golden(name)
-    ptr, idx, deg, gid, G = BatchGraph.build_host(g.graphs, g.P)
+    h = BatchGraph.build_host(g.graphs, g.P)
+    ptr, idx, deg, gid, G = h.ev_ptr, h.ev_idx, h.deg, h.graph_id, h.n_graphs
     uniq = []
     for gr in g.graphs:
         if not any(gr is u for u in uniq):
@@ -60,6 +62,7 @@ def test_event_csr_matches_oracle(name):
             assert idx[ptr[node]:ptr[node + 1]].tolist() == ev[p]
             assert deg[node] == len(list(gr.neighbors(p)))
             assert len(ev[p]) == 2 * deg[node]
+            assert h.adj_idx[h.adj_ptr[node]:h.adj_ptr[node + 1]].tolist() == list(gr.neighbors(p))
     if gid is not None:
         assert [uniq[i] is gr for i, gr in zip(gid, g.graphs)] == [True] * g.B
 
@@ -69,8 +72,10 @@ def test_self_loop_and_isolated_node():
     gr = nx.Graph()
     gr.add_nodes_from(range(4))
     gr.add_edges_from([(0, 1), (1, 1), (1, 2)])          # node 3 isolated, self-loop on 1
-    ptr, idx, deg, gid, G = BatchGraph.build_host([gr, gr], 4)
+    h = BatchGraph.build_host([gr, gr], 4)
+    ptr, idx, deg, gid, G = h.ev_ptr, h.ev_idx, h.deg, h.graph_id, h.n_graphs
     assert gid is None and G == 1
+    assert h.adj_idx[h.adj_ptr[1]:h.adj_ptr[2]].tolist() == [0, 2] and h.max_adj == 4 and h.max_events == 10
     assert deg.tolist() == [1, 3, 1, 0]
     assert idx[ptr[3]:ptr[4]].tolist() == []
     y = torch.randn(1, 4, 6, 1)

@@ -353,3 +353,38 @@ def test_unfolded_tc_vs_simt_vs_fp64_oracle(a_scale):
     print(f"a_scale={a_scale}: Y[K-1] rel-L2 vs fp64: simt={rel_l2(outs['simt'][0][-1], Y64[-1]):.2e} "
           f"tc={rel_l2(outs['tc'][0][-1], Y64[-1]):.2e}; grad tc vs simt={rel_l2(g_t, g_s):.2e}")
     assert rel_l2(g_t, g_s) < max(1e-4, 50 * rel_l2(outs["tc"][0][-1], outs["simt"][0][-1]))
+
+
+# ------------------------------------------------------------------------------------------ fused K-loop vs single steps
+@pytest.mark.parametrize("name", MODEL1_CASES)
+def test_fused_levels_equal_chain_of_single_steps(name):
+    """dadmm_unfolded_fwd/bwd (re-associated "level" kernels) against the same recurrence driven one iteration at a
+    time through dadmm_contract + dadmm_step_fwd/bwd under autograd: Y bit-identical, d/d hyp to 1e-5."""
+    DF, BG = _df()
+    g = Golden(name)
+    A = g.t("A")
+    AtA, Atb = O.atx(A, A), O.atx(A, g.t("b"))
+    W = AtA[0].contiguous().to(DEV)
+    Wt = W.transpose(1, 2).contiguous()
+    graph = BG.from_graph_list(g.graphs, g.P, DEV)
+    hyp0 = _hyp_for(g).to(DEV)
+    K = hyp0.shape[0]
+    clamps = [DF.clamps_model1(k) for k in range(K)]
+    gen = torch.Generator().manual_seed(9)
+    gY = torch.randn((K, g.B, g.P, g.n, 1), generator=gen).to(DEV) * 1e-3
+    # fused
+    h1 = hyp0.clone().requires_grad_(True)
+    Y1 = DF.Unfolded.apply(h1, W, Wt, _dev(Atb), _dev(g.t("y0")), _dev(g.t("U0")), _dev(g.t("d0")), graph, clamps, "simt", None, None)
+    (Y1 * gY).sum().backward()
+    # chain
+    h2 = hyp0.clone().requires_grad_(True)
+    y, U, d = _dev(g.t("y0")), _dev(g.t("U0")), _dev(g.t("d0"))
+    Ys = []
+    for k in range(K):
+        a = DF.Contract.apply(y, W, Wt, "simt")
+        y, U, d = DF.Step.apply(y, U, d, a, _dev(Atb), h2[k], graph, clamps[k], None)
+        Ys.append(y)
+    Y2 = torch.stack(Ys).unsqueeze(-1)
+    (Y2 * gY).sum().backward()
+    assert torch.equal(Y1, Y2)
+    assert rel_l2(h1.grad.cpu(), h2.grad.cpu()) < 1e-5
