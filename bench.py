@@ -202,10 +202,11 @@ def run_ours(opt, w):
         loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False, global_batch=B_glob)
         optim.zero_grad(set_to_none=True)
         loss_final.backward()
+        loss_val = loss_final.detach().clone()
         if world > 1:
-            D.allreduce_gradients(model)
+            D.allreduce_gradients(model, extra=[loss_val])      # gradients + loss reduction, one NCCL bucket
         optim.step()
-        return loss_final
+        return loss_val
 
     def barrier():
         torch.cuda.synchronize()

@@ -53,7 +53,8 @@ def allreduce_sum_(tensors: Iterable[torch.Tensor], group=None) -> None:
         off += k
 
 
-def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
-    """Sum parameter gradients over ranks.  With ``compute_loss(..., global_batch=B_total)`` each rank's loss
-    is its share of the global mean, so the summed gradients equal the single-process gradient."""
-    allreduce_sum_([p.grad for p in module.parameters() if p.grad is not None], group)
+def allreduce_gradients(module: torch.nn.Module, extra=(), group=None) -> None:
+    """Sum parameter gradients (and any ``extra`` tensors, e.g. the detached per-rank loss shares) over ranks in
+    one bucket.  With ``compute_loss(..., global_batch=B_total)`` each rank's loss is its share of the global mean,
+    so the summed gradients equal the single-process gradient and the summed losses equal the global loss."""
+    allreduce_sum_([p.grad for p in module.parameters() if p.grad is not None] + list(extra), group)
