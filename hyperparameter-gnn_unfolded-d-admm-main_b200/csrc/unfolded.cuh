@@ -122,8 +122,15 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
     return k;
 }
 
+#ifndef DADMM_LEVEL_MINB_FWD
+#define DADMM_LEVEL_MINB_FWD 4      // round-1 sweep on B200 (cfg4): 1 -> 1.34 ms, 3 -> 1.28, 4 -> 1.17 per level
+#endif
+#ifndef DADMM_LEVEL_MINB_BWD
+#define DADMM_LEVEL_MINB_BWD 3      // 1 -> 2.45 ms, 2 -> 2.34, 3 -> 2.29, 4 -> 2.76 (spills)
+#endif
+
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads) level_fwd_kernel(const LevelFwdParams<T> p) {
+__global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_kernel(const LevelFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(kStepThreads) level_fwd_kernel(const LevelFwdP
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads) level_bwd_kernel(const LevelBwdParams<T> p) {
+__global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_kernel(const LevelBwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
