@@ -1,0 +1,392 @@
+// contract_f16.cuh -- fp32-accurate contraction on the kind::f16 tensor path (twice the tf32 rate).
+//
+//   out[b,p,:] (+)= W_p x[b,p,:]          (same operation as contract_tc.cuh / contract_simt.cuh)
+//
+// Every fp32 operand value v is represented as  v * 2^e = hi + lo  with hi = rn_fp16(v 2^e) and
+// lo = rn_fp16(v 2^e - hi): 22 significant bits, both halves round-to-nearest (the tf32 split of
+// contract_tc.cuh truncates hi), and e is ONE power of two per tensor, chosen from the tensor's max |v| so
+// that hi stays in fp16's normal range.  A global scale commutes with the contraction, so the result is
+// exact up to the dropped lo*lo term (2^-22) -- measured 7e-8 relative vs fp64 for the products, i.e. the fp32
+// rounding of the accumulation dominates.  Three MMAs per k-step (lo*hi, hi*lo, hi*hi) at the f16 rate cost
+// half of the 3xTF32 scheme, and because the operands arrive in global memory already split
+// (split_f16_kernel; W once per operator, x by its producer), the GEMM kernel has no conversion stage:
+// TMA -> shared memory -> tcgen05.mma, 80 KB of shared-memory traffic per 768 MMA cycles instead of 144 KB.
+//
+// Accumulation is chunked exactly as in contract_tc.cuh (64 k per tensor-core partial sum, fp32 RN adds in
+// registers) because the TMEM accumulator truncates.  CTA pairs (cta_group::2), 256 x 256 output tile per pair.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "contract_tc.cuh"
+
+namespace dadmm {
+namespace f16 {
+
+using tc::A_BYTES;   // 128 rows x 64 bytes
+constexpr int BKE = 32;                          // k elements per k-block (64-byte fp16 rows, SWIZZLE_64B)
+constexpr int STAGES = 6;
+constexpr int TILE = A_BYTES;                    // every operand tile: 128 rows x 64 B = 8 KB
+constexpr int STAGE = 4 * TILE;                  // A_hi | B_hi | A_lo | B_lo
+constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+constexpr int THREADS = 384;                     // warps 0-3: TMA, MMA, (2 idle); warps 4-11: accumulate + store
+constexpr int EPI_WARP0 = 4;
+#ifndef DADMM_F16_KB_PER_CHUNK
+#define DADMM_F16_KB_PER_CHUNK 2
+#endif
+constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;   // 2 x 32 = 64 k per tensor-core partial sum
+constexpr int COLS_PER_THREAD = 128;
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------------
+// max |x| over a tensor as raw float bits (non-negative floats order like unsigned ints)
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out) {
+    unsigned m = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n) {
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+        } else {
+            for (long long j = i; j < n; ++j) m = max(m, __float_as_uint(fabsf(x[j])));
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// exponent e with max|v| * 2^e in [2^13, 2^14): two bits of head-room below fp16's 65504
+__device__ __forceinline__ int scale_exponent(unsigned amax_bits) {
+    const int ea = (int)((amax_bits >> 23) & 0xFF) - 127;          // floor(log2(amax)); amax == 0 or denormal -> -127
+    if (ea <= -100 || ea >= 128) return 0;                          // all zeros / non-finite: leave unscaled
+    return 13 - ea;
+}
+__device__ __forceinline__ float pow2f(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }
+
+// x [rows][n] fp32 (row stride ld) -> hi, lo [rows][n_pad] fp16 with the tensor's scale; writes the exponent
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, long long rows, int n, long long ld,
+                                                        int n_pad, const unsigned* __restrict__ amax_bits,
+                                                        __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ exp_out) {
+    const int e = scale_exponent(*amax_bits);
+    // 2^e can exceed the float range for tiny tensors; apply it in two factors
+    const float s1 = pow2f(e / 2), s2 = pow2f(e - e / 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+        const float* xr = x + r * ld;
+        __half* hr = hi + r * n_pad;
+        __half* lr = lo + r * n_pad;
+        for (int i = lane * 2; i < n_pad; i += 64) {
+            float v0 = (i < n) ? xr[i] : 0.f, v1 = (i + 1 < n) ? xr[i + 1] : 0.f;
+            v0 = v0 * s1 * s2;
+            v1 = v1 * s1 * s2;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            *reinterpret_cast<__half2*>(hr + i) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(lr + i) = __halves2half2(l0, l1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GEMM kernel
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+
+struct Params {
+    int B, P, n_out, n_in;
+    float* out;
+    long long o_sb;
+    int accumulate;
+    int m_tiles, n_tiles, k_blocks, total_tiles;
+    const int *exp_w, *exp_x;      // device: scale exponents of the two operands
+    unsigned* amax_out;            // device, optional: running max |out| bits (feeds the next operand split's bound)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                    const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Params p) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto stage_base = [&](int s) { return base + (uint32_t)s * STAGE; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);       // leader: one expect_tx arrival, bytes from both CTAs' TMA
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 16);    // 8 accumulate warps per CTA x 2 CTAs (leader only)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int tiles_per_agent = p.m_tiles * p.n_tiles;
+    const int n_chunks = (p.k_blocks + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+
+    if (warp < EPI_WARP0) {
+        reg_dec<40>();
+        if (warp == 0 && lane == 0) {
+            // -------------------------------------------------------------- TMA producer
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
+                const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * 256 + (int)rank * 128;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t lead = full_bar(stage) & 0xFEFFFFFFu;     // same offset in the pair's leader CTA
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);
+                    const uint32_t sb = stage_base(stage);
+                    tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
+                    tma_load_3d_pair(sb + TILE, &map_xh, lead, kb * BKE, ag, b0);
+                    tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
+                    tma_load_3d_pair(sb + 3 * TILE, &map_xl, lead, kb * BKE, ag, b0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else if (warp == 1 && lane == 0 && rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (leader CTA)
+            int stage = 0;
+            uint32_t phase = 0;
+            int ci = 0;
+            for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait(tempty_bar(buf), ((uint32_t)(ci >> 1) & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256;
+                    const int kb_end = min(p.k_blocks, (ch + 1) * KB_PER_CHUNK);
+                    for (int kb = ch * KB_PER_CHUNK; kb < kb_end; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tcgen05_fence_after();
+                        const uint32_t sa = stage_base(stage), sb = sa + TILE, sa_lo = sa + 2 * TILE, sb_lo = sa + 3 * TILE;
+#pragma unroll
+                        for (int ks = 0; ks < BKE / 16; ++ks) {
+                            const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the 64-byte swizzled row
+                            const uint64_t da = umma_desc(sa + koff), db = umma_desc(sb + koff);
+                            const uint64_t da_lo = umma_desc(sa_lo + koff), db_lo = umma_desc(sb_lo + koff);
+                            umma_f16_pair(d_tmem, da_lo, db, (kb != ch * KB_PER_CHUNK) || ks != 0);
+                            umma_f16_pair(d_tmem, da, db_lo, 1u);
+                            umma_f16_pair(d_tmem, da, db, 1u);
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit_pair(tfull_bar(buf));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ accumulate + store (256 threads per CTA)
+        reg_inc<216>();
+        const int q = warp & 3;
+        const int h = (warp - EPI_WARP0) >> 2;
+        const int es = -(__ldg(p.exp_w) + __ldg(p.exp_x));           // undo both operand scales (exact: powers of two)
+        const float unscale = pow2f(es / 2), unscale2 = pow2f(es - es / 2);
+        const float rescale = pow2f(-es / 2), rescale2 = pow2f(-es + es / 2);
+        int ci = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
+            const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * 256 + h * COLS_PER_THREAD;
+            float acc[COLS_PER_THREAD];
+            const int i = i0 + q * 32 + lane;
+            float* orow = p.out + (long long)ag * p.n_out + i;
+            if (p.accumulate) {
+                // out += W x: seed the accumulators with the old values in the SCALED domain (power-of-two factors,
+                // exact); the loads fly while the tensor core works on the first chunk
+#pragma unroll
+                for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                    const int b = b0 + c;
+                    acc[c] = (i < p.n_out && b < p.B) ? __ldcs(orow + (long long)b * p.o_sb) * rescale * rescale2 : 0.0f;
+                }
+            }
+            for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait(tfull_bar(buf), (uint32_t)(ci >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * COLS_PER_THREAD);
+                const bool seed = (ch == 0) && !p.accumulate;
+#if defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT >= 1
+                if (p.n_in < 0 || ch == 0)   // timing experiment: drain only the first chunk
+#endif
+#pragma unroll
+                for (int j = 0; j < COLS_PER_THREAD / 32; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32u * j, v);
+                    tmem_ld_wait();
+                    if (seed) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[32 * j + c] = __uint_as_float(v[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[32 * j + c] += __uint_as_float(v[c]);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_bar(buf), 0);
+            }
+            unsigned amax_bits = 0;
+            if (i < p.n_out) {
+#pragma unroll
+                for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                    const int b = b0 + c;
+                    if (b < p.B) {
+                        const float val = acc[c] * unscale * unscale2;
+                        orow[(long long)b * p.o_sb] = val;
+                        amax_bits = max(amax_bits, __float_as_uint(fabsf(val)));
+                    }
+                }
+            }
+            if (p.amax_out) {
+                amax_bits = __reduce_max_sync(0xffffffffu, amax_bits);
+                if (lane == 0 && amax_bits > *reinterpret_cast<volatile unsigned*>(p.amax_out)) atomicMax(p.amax_out, amax_bits);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+inline int pad8(int n) { return (n + 7) / 8 * 8; }
+
+// split layout of a tensor with `rows` rows of n values: [scalars 256 B | hi rows*n_pad fp16 | lo rows*n_pad fp16]
+struct Split {
+    unsigned* amax;
+    int* exp;
+    __half *hi, *lo;
+};
+inline size_t split_bytes(long long rows, int n) { return 256 + ((size_t)rows * pad8(n) * 2 * 2 + 255) / 256 * 256; }
+inline Split split_view(void* base, long long rows, int n) {
+    char* c = (char*)base;
+    Split s;
+    s.amax = (unsigned*)c;
+    s.exp = (int*)(c + 16);
+    s.hi = (__half*)(c + 256);
+    s.lo = s.hi + (size_t)rows * pad8(n);
+    return s;
+}
+
+// x [rows][n] (row stride ld) -> split buffer (amax pass + split pass)
+inline int split_tensor(const float* x, long long rows, int n, long long ld, void* buf, cudaStream_t s) {
+    Split v = split_view(buf, rows, n);
+    DADMM_CUDA(cudaMemsetAsync(v.amax, 0, 32, s));
+    ProfScope prof(PROF_SPLIT, s);
+    if (ld == n) {
+        const long long tot = rows * n;
+        const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(tot, 1024));
+        amax_kernel<<<nblk, 256, 0, s>>>(x, tot, v.amax);
+    } else {
+        for (long long r = 0; r < rows; ++r) amax_kernel<<<1, 256, 0, s>>>(x + r * ld, n, v.amax);   // strided rows: rare
+    }
+    DADMM_LAUNCHED();
+    const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
+    split_f16_kernel<<<nblk, 256, 0, s>>>(x, rows, n, ld, pad8(n), v.amax, v.hi, v.lo, v.exp);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+inline bool dims_supported(int B, int P, int n_out, int n_in) { return B >= 128 && n_out > 128 && n_in >= 32 && P >= 1; }
+
+inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
+                   cuuint64_t s1, cuuint64_t s2, cuuint32_t b0, cuuint32_t b1, cuuint32_t b2) {
+    cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, b2}, es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DADMM_FAIL(-4, "cuTensorMapEncodeTiled(f16) failed: %d", (int)r);
+    return 0;
+}
+
+// out[b,p,:] (+)= W_p x[b,p,:] from prepared operands: wprep = split of W viewed as [P*n_out][n_in],
+// xprep = split of x viewed as [B*P][n_in]
+inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
+                  cudaStream_t s, unsigned* amax_out = nullptr) {
+    tc::EncodeTiledFn enc = tc::encode_fn();
+    if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
+    const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
+    const cuuint64_t np = pad8(n_in);
+    CUtensorMap mwh, mwl, mxh, mxl;
+    if (int e = encode3(enc, &mwh, w.hi, n_in, n_out, P, np * 2, (cuuint64_t)n_out * np * 2, BKE, 128, 1)) return e;
+    if (int e = encode3(enc, &mwl, w.lo, n_in, n_out, P, np * 2, (cuuint64_t)n_out * np * 2, BKE, 128, 1)) return e;
+    if (int e = encode3(enc, &mxh, x.hi, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, 128)) return e;
+    if (int e = encode3(enc, &mxl, x.lo, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, 128)) return e;
+    Params p;
+    p.B = B; p.P = P; p.n_out = n_out; p.n_in = n_in;
+    p.out = out; p.o_sb = o_sb; p.accumulate = accumulate;
+    p.m_tiles = ceil_div(n_out, 256);
+    p.n_tiles = ceil_div(B, 256);
+    p.k_blocks = ceil_div(n_in, BKE);
+    p.total_tiles = P * p.m_tiles * p.n_tiles;
+    p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out;
+    static int num_sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    static bool attr_set = false;
+    if (!attr_set) {
+        DADMM_CUDA(cudaFuncSetAttribute(contract_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const int clusters = std::min(num_sms / 2, p.total_tiles);
+    ProfScope prof(PROF_CONTRACT_TC, s);
+    contract_f16_kernel<<<2 * clusters, THREADS, SMEM, s>>>(mwh, mwl, mxh, mxl, p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+}  // namespace f16
+}  // namespace dadmm

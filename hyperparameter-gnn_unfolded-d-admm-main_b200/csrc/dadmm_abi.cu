@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "contract_simt.cuh"
 #include "contract_tc.cuh"
+#include "contract_f16.cuh"
 #include "step.cuh"
 #include "unfolded.cuh"
 
@@ -207,31 +208,60 @@ static int bwd_nchunks(int dtype, int B, int P, int n, int* out) {
     return 0;
 }
 
+// Which kernel serves a contraction call (AUTO: f16 pairs > tf32 > FMA, by shape / layout support).
+static int resolve_algo(int dtype, int algo, int B, int P, int n_out, int n_in, bool tc_layout) {
+    if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return DADMM_ALGO_SIMT;
+    const bool f16_ok = tc_layout && f16::dims_supported(B, P, n_out, n_in);
+    const bool tf32_ok = tc_layout && tc::dims_supported(B, P, n_out, n_in);
+    if (algo == DADMM_ALGO_TC_3XF16) return f16_ok ? DADMM_ALGO_TC_3XF16 : -1;
+    if (algo == DADMM_ALGO_TC_3XTF32) return tf32_ok ? DADMM_ALGO_TC_3XTF32 : -1;
+    static const int prefer = [] {                       // DADMM_TC_PREFER=tf32 keeps AUTO on the 3xTF32 kernels
+        const char* e = getenv("DADMM_TC_PREFER");
+        return (e && !strcmp(e, "tf32")) ? DADMM_ALGO_TC_3XTF32 : DADMM_ALGO_TC_3XF16;
+    }();
+    if (f16_ok && prefer == DADMM_ALGO_TC_3XF16) return DADMM_ALGO_TC_3XF16;
+    if (tf32_ok) return DADMM_ALGO_TC_3XTF32;
+    return DADMM_ALGO_SIMT;
+}
+
+static size_t contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in) {
+    if (resolve_algo(dtype, algo, B, P, n_out, n_in, true) != DADMM_ALGO_TC_3XF16) return 0;
+    return f16::split_bytes((long long)P * n_out, n_in) + f16::split_bytes((long long)B * P, n_in);
+}
+
+// w_prepared: the fp16 split of W already sits at the head of `ws` (K-loop drivers split the operator once)
 static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in, const void* W, int64_t w_sp,
                          int64_t w_si, int64_t w_sk, const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk,
                          void* out, int64_t o_sb, int64_t o_sp, int64_t o_si, int accumulate, void* ws,
-                         size_t ws_bytes, cudaStream_t s) {
+                         size_t ws_bytes, cudaStream_t s, bool w_prepared = false) {
     if (B <= 0 || P <= 0 || n_out <= 0 || n_in <= 0) DADMM_FAIL(-1, "contract: bad dims");
     if (!W || !x || !out) DADMM_FAIL(-1, "contract: null pointer");
-    if (dtype == DADMM_F32) {
-        const bool tc_ok = tc::shape_supported(B, P, n_out, n_in, W, w_sp, w_si, w_sk, x, x_sb, x_sp, x_sk, out, o_sb,
-                                               o_sp, o_si);
-        if (algo == DADMM_ALGO_TC_3XTF32 && !tc_ok) DADMM_FAIL(-4, "contract: shape/layout not supported by the tcgen05 kernel");
-        if (tc_ok && (algo == DADMM_ALGO_TC_3XTF32 || algo == DADMM_ALGO_AUTO))
-            return tc::launch(B, P, n_out, n_in, (const float*)W, (const float*)x, (float*)out, x_sb, o_sb, accumulate, ws,
-                              ws_bytes, s);
-        GemmParams<float> p{B, P, n_out, n_in, (const float*)W, w_sp, w_si, w_sk, (const float*)x, x_sb, x_sp, x_sk,
-                            (float*)out, o_sb, o_sp, o_si, accumulate};
-        return launch_contract_simt<float>(p, s);
-    } else if (dtype == DADMM_F64) {
-        if (algo == DADMM_ALGO_TC_3XTF32) DADMM_FAIL(-4, "contract: tcgen05 path is fp32 only");
+    if (dtype != DADMM_F32 && dtype != DADMM_F64) DADMM_FAIL(-1, "contract: unknown dtype %d", dtype);
+    if (dtype == DADMM_F64) {
+        if (algo == DADMM_ALGO_TC_3XTF32 || algo == DADMM_ALGO_TC_3XF16) DADMM_FAIL(-4, "contract: tensor-core paths are fp32 only");
         GemmParams<double> p{B, P, n_out, n_in, (const double*)W, w_sp, w_si, w_sk, (const double*)x, x_sb, x_sp, x_sk,
                              (double*)out, o_sb, o_sp, o_si, accumulate};
         return launch_contract_simt<double>(p, s);
     }
-    DADMM_FAIL(-1, "contract: unknown dtype %d", dtype);
+    const bool tc_layout = tc::shape_supported(std::max(B, 128), P, std::max(n_out, 64), std::max(n_in, 16), W, w_sp, w_si, w_sk, x,
+                                               x_sb, x_sp, x_sk, out, o_sb, o_sp, o_si);
+    const int ra = resolve_algo(dtype, algo, B, P, n_out, n_in, tc_layout && x_sb == (int64_t)P * n_in);
+    if (ra < 0) DADMM_FAIL(-4, "contract: shape/layout not supported by the requested tensor-core kernel");
+    if (ra == DADMM_ALGO_TC_3XF16) {
+        const size_t wb = f16::split_bytes((long long)P * n_out, n_in), xb = f16::split_bytes((long long)B * P, n_in);
+        if (!ws || ws_bytes < wb + xb) DADMM_FAIL(-1, "contract: workspace too small for the fp16 operand copies");
+        char* c = (char*)ws;
+        if (!w_prepared)
+            if (int e = f16::split_tensor((const float*)W, (long long)P * n_out, n_in, n_in, c, s)) return e;
+        if (int e = f16::split_tensor((const float*)x, (long long)B * P, n_in, n_in, c + wb, s)) return e;
+        return f16::launch(B, P, n_out, n_in, c, c + wb, (float*)out, o_sb, accumulate, s);
+    }
+    if (ra == DADMM_ALGO_TC_3XTF32)
+        return tc::launch(B, P, n_out, n_in, (const float*)W, (const float*)x, (float*)out, x_sb, o_sb, accumulate, ws, ws_bytes, s);
+    GemmParams<float> p{B, P, n_out, n_in, (const float*)W, w_sp, w_si, w_sk, (const float*)x, x_sb, x_sp, x_sk,
+                        (float*)out, o_sb, o_sp, o_si, accumulate};
+    return launch_contract_simt<float>(p, s);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // level kernels of the fused K-iteration path (unfolded.cuh)
@@ -257,8 +287,9 @@ template <typename T>
 static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, const void* y,
                           const void* U_in, const void* d0, const void* a, const void* atb, void* y_next, void* U_out,
-                          void* graw, int32_t* flags, cudaStream_t s) {
+                          void* graw, int32_t* flags, const SplitOut& sp, cudaStream_t s) {
     LevelFwdParams<T> p;
+    p.sp = sp;
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr);
     p.lst_ptr = g->ev_ptr; p.lst_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
@@ -299,8 +330,10 @@ template <typename T>
 static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, int top, const void* y,
                           const void* U_prev, const void* d0, const void* graw, void* Tb, void* C, void* ga,
-                          const void* gY_prev, const void* label, double coef_prev, void* partials, cudaStream_t s) {
+                          const void* gY_prev, const void* label, double coef_prev, void* partials, const SplitOut& sp,
+                          cudaStream_t s) {
     LevelBwdParams<T> p;
+    p.sp = sp;
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr); p.top = top;
     p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx; p.deg = g->deg; p.gid = g->graph_id;
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
@@ -341,6 +374,13 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     return 0;
 }
 
+static size_t amax_slots_bytes(int K) { return ((size_t)(K + 1) * 4 + 255) / 256 * 256; }
+
+// the fused fp16 path: operands of the contraction are produced already split by the level kernels
+static bool fused_f16(int dtype, int algo, int B, int P, int n) {
+    return dtype == DADMM_F32 && (n % 8) == 0 && resolve_algo(dtype, algo, B, P, n, n, true) == DADMM_ALGO_TC_3XF16;
+}
+
 template <typename T>
 static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
                              const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb, const void* y0,
@@ -348,25 +388,41 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                              cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
-    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;
     char* a = w8 + cw;
     char* pp[2] = {a + NBa, a + 2 * NBa};
+    unsigned* slots = (unsigned*)(a + 3 * NBa);     // max|y_k| bits, k = 0..K
     const int64_t sn = n, sPn = (int64_t)P * n;
     const size_t row = (size_t)P * 4 * es;
+    const bool fused = fused_f16(dtype, algo, B, P, n);
+    const size_t wb = fused ? f16::split_bytes((long long)P * n, n) : 0;
+    f16::Split xs{};
+    if (fused) {
+        xs = f16::split_view(w8 + wb, (long long)B * P, n);
+        DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
+        if (int e = f16::split_tensor((const float*)W, (long long)P * n, n, n, w8, s)) return e;
+        if (int e = f16::split_tensor((const float*)y0, (long long)B * P, n, n, w8 + wb, s)) return e;
+    }
     for (int k = 0; k < K; ++k) {
         const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
         // U_j for j >= 1 lives in U_save[j-1] (training) or in a ping-pong buffer (inference)
         auto Uslot = [&](int j) -> char* { return U_save ? (char*)U_save + (size_t)(j - 1) * NB : pp[j & 1]; };
         const char* Uin = (k <= 1) ? (const char*)U0 : Uslot(k - 1);
         char* Uout = (k == 0 || k == K - 1) ? nullptr : Uslot(k);   // U_{K-1} is consumed in-register only
-        if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, w8, cw, s))
-            return e;
+        SplitOut sp{};
+        if (fused) {
+            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)a, sPn, 0, s)) return e;
+            if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
+        } else {
+            if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, w8, cw, s, k > 0))
+                return e;
+        }
         if (int e = level_fwd_impl<T>(dtype, B, P, n, graph, clamps + k, k ? clamps + k - 1 : nullptr, (const char*)hyp + k * row,
                                       k ? (const char*)hyp + (k - 1) * row : nullptr, yk, Uin, d0, a, Atb,
                                       (char*)Y + (size_t)k * NB, Uout, R_save ? (char*)R_save + (size_t)k * NB : nullptr,
-                                      flags ? flags + k : nullptr, s))
+                                      flags ? flags + k : nullptr, sp, s))
             return e;
     }
     return 0;
@@ -379,22 +435,33 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                              const void* label, const double* loss_coef, void* ghyp, void* ws, cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
-    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;
     char *Tb = w8 + cw, *C = Tb + NBa, *ga = C + NBa, *part = ga + NBa;
+    unsigned* slots = (unsigned*)(part + (partials_elems(B, P, n) * es + 255) / 256 * 256);   // max|adj(y_{k+1})| bits
     const int64_t sn = n, sPn = (int64_t)P * n;
     const size_t row = (size_t)P * 4 * es;
-    const bool fused = label && loss_coef;
+    const bool with_loss = label && loss_coef;
+    const bool fused = fused_f16(dtype, algo, B, P, n);
+    const size_t wb = fused ? f16::split_bytes((long long)P * n, n) : 0;
+    f16::Split xs{};
     DADMM_CUDA(cudaMemsetAsync(ghyp, 0, (size_t)K * row, s));
+    if (fused) {
+        xs = f16::split_view(w8 + wb, (long long)B * P, n);
+        DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
+        if (K > 1)
+            if (int e = f16::split_tensor((const float*)Wt, (long long)P * n, n, n, w8, s)) return e;
+    }
     {   // adjoint of y_K
         const long long rows = (long long)B * P;
         const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
         ProfScope prof(PROF_LOSS, s);
         seed_adjoint_kernel<T><<<nblk, 256, 0, s>>>((const T*)((const char*)Y + (size_t)(K - 1) * NB),
                                                    gY ? (const T*)((const char*)gY + (size_t)(K - 1) * NB) : nullptr,
-                                                   (fused && loss_coef[K - 1] != 0.0) ? (const T*)label : nullptr,
-                                                   (T)(fused ? loss_coef[K - 1] : 0.0), B, P, n, (T*)Tb);
+                                                   (with_loss && loss_coef[K - 1] != 0.0) ? (const T*)label : nullptr,
+                                                   (T)(with_loss ? loss_coef[K - 1] : 0.0), B, P, n, (T*)Tb,
+                                                   fused ? slots + (K - 1) : nullptr);
         DADMM_LAUNCHED();
     }
     int nchunks = 0;
@@ -402,11 +469,13 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     for (int k = K - 1; k >= 0; --k) {
         const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
         const char* Uprev = (k <= 1) ? (const char*)U0 : (const char*)U_save + (size_t)(k - 2) * NB;   // U_{k-1}
+        SplitOut sp{};
+        if (fused && k > 0) sp = SplitOut{xs.hi, xs.lo, xs.exp, slots + k, nullptr};
         if (int e = level_bwd_impl<T>(dtype, B, P, n, graph, clamps + k, k ? clamps + k - 1 : nullptr, (const char*)hyp + k * row,
                                       k ? (const char*)hyp + (k - 1) * row : nullptr, k == K - 1, yk, Uprev, d0,
                                       (const char*)R_save + (size_t)k * NB, Tb, C, ga,
                                       (gY && k) ? (const char*)gY + (size_t)(k - 1) * NB : nullptr, label,
-                                      (fused && k) ? loss_coef[k - 1] : 0.0, part, s))
+                                      (with_loss && k) ? loss_coef[k - 1] : 0.0, part, sp, s))
             return e;
         {
             ProfScope prof(PROF_REDUCE_HYP, s);
@@ -415,8 +484,13 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
             DADMM_LAUNCHED();
         }
         if (k > 0) {
-            if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s))
-                return e;
+            if (fused) {
+                if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)Tb, sPn, 1, s, slots + (k - 1))) return e;
+            } else {
+                if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s,
+                                          k < K - 1))
+                    return e;
+            }
         }
     }
     return 0;
@@ -477,13 +551,12 @@ int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in, const
 }
 
 size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in) {
-    if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return 0;
-    return tc::workspace_bytes(B, P, n_out, n_in);
+    return contract_ws_bytes(dtype, algo, B, P, n_out, n_in);
 }
 
 int dadmm_contract_uses_tensor_cores(int dtype, int algo, int B, int P, int n_out, int n_in) {
-    if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return 0;
-    return tc::dims_supported(B, P, n_out, n_in) ? 1 : 0;
+    const int ra = resolve_algo(dtype, algo, B, P, n_out, n_in, true);
+    return (ra == DADMM_ALGO_TC_3XTF32 || ra == DADMM_ALGO_TC_3XF16) ? ra : 0;
 }
 
 int dadmm_step_fwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,
@@ -542,12 +615,11 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
 }
 
 size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward) {
-    (void)K;
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t NBa = ((size_t)B * P * n * es + 255) / 256 * 256;
-    const size_t cw = (dadmm_contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
-    if (!backward) return cw + 3 * NBa;                                   // AtAy + two U ping-pong buffers
-    return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256;     // T, C, gAtAy + partials
+    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    if (!backward) return cw + 3 * NBa + amax_slots_bytes(K);             // AtAy + two U ping-pong buffers + amax slots
+    return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256 + amax_slots_bytes(K);   // T, C, gAtAy, partials
 }
 
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,

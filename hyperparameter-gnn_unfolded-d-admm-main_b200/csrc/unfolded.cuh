@@ -27,9 +27,66 @@
 // shared-memory work (register double buffering), and the four hyper-parameter partial sums share one
 // 6-shuffle reduction.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "step.cuh"
 
 namespace dadmm {
+
+// Optional fused operand split for the fp16 tensor-core contraction (contract_f16.cuh): the producer of a GEMM
+// operand writes it as scaled fp16 (hi, lo) pairs, so the GEMM needs no conversion pass.  The scale is a power
+// of two derived from a RIGOROUS bound of the tensor's max |v| that every CTA computes identically:
+//   forward : |y_{k+1}| <= min(V_k, max|y_k| + max_p(alpha_p) * G_k)
+//   backward: |gAtAy_k| <= max_p(alpha_p) * max|adj(y_{k+1})|
+// (max|y_k| / max|adj| are tracked with one atomicMax per CTA by the kernels that produce those tensors).
+struct SplitOut {
+    __half *hi, *lo;          // [B*P][n] fp16 each (n % 8 == 0), nullptr = no split output
+    int* exp;                 // device: scale exponent written for the GEMM epilogue
+    const unsigned* amax_in;  // device: max |.| bits of the tensor the bound is derived from (nullptr = use the clamp bound)
+    unsigned* amax_out;       // device: running max |.| bits of the tensor this kernel produces (nullptr = not tracked)
+};
+
+__device__ __forceinline__ int split_exponent(float bound) {
+    const unsigned bits = __float_as_uint(bound);
+    const int ea = (int)((bits >> 23) & 0xFF) - 127;
+    if (ea <= -100 || ea >= 128) return 0;
+    return 13 - ea;                                   // bound * 2^e in [2^13, 2^14)
+}
+__device__ __forceinline__ float pow2_of(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }
+
+template <int VEC>
+__device__ __forceinline__ void store_split(const SplitOut& sp, size_t off, const Vec<float, VEC>& v, float s1, float s2) {
+    __half h[VEC], l[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const float x = v.v[j] * s1 * s2;
+        h[j] = __float2half_rn(x);
+        l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<uint2*>(sp.hi + off) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(sp.lo + off) = *reinterpret_cast<const uint2*>(l);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            sp.hi[off + j] = h[j];
+            sp.lo[off + j] = l[j];
+        }
+    }
+}
+
+// CTA-wide max of per-thread |.| bits -> at most one atomicMax per CTA
+__device__ __forceinline__ void publish_amax(unsigned m, unsigned* out, unsigned* sh /*[32]*/) {
+    m = __reduce_max_sync(0xffffffffu, m);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = max(t, sh[w]);
+        if (t > *reinterpret_cast<volatile unsigned*>(out)) atomicMax(out, t);
+    }
+}
 
 template <typename T>
 struct LevelFwdParams {
@@ -41,6 +98,7 @@ struct LevelFwdParams {
     const T *y, *U_in, *d0, *a, *atb;
     T *y_next, *U_out, *graw;
     int32_t* flags;
+    SplitOut sp;                        // fp16 split of y_{k+1} (fp32 only)
 };
 
 template <typename T>
@@ -55,6 +113,7 @@ struct LevelBwdParams {
     const T *gY_prev, *label;
     T coef_prev;
     T* partials;
+    SplitOut sp;                        // fp16 split of gAtAy_k; sp.amax_in = max|adj(y_{k+1})|
 };
 
 // Stage the neighbour lists of the tile's problems: sPtr[bl][0..P] = list bounds relative to sIdx[bl],
@@ -146,6 +205,27 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     const int i = chunk * CH + lane * VEC;
     const bool act_i = i < p.n;
     const bool first = p.first != 0;
+    __shared__ unsigned sAmax[32];
+
+    // scale of the fused fp16 split of y_{k+1} (identical in every CTA)
+    float sc1 = 1.f, sc2 = 1.f;
+    bool do_split = false;
+    if constexpr (sizeof(T) == 4) {
+        do_split = p.sp.hi != nullptr;
+        if (do_split) {
+            float bound = (float)p.V;
+            if (p.sp.amax_in) {
+                float amax_alpha = 0.f;
+                for (int q = 0; q < P; ++q) amax_alpha = fmaxf(amax_alpha, fabsf((float)__ldg(p.hyp_k + q * 4)));
+                bound = fminf(bound, __uint_as_float(__ldg(p.sp.amax_in)) + amax_alpha * (float)p.G);
+            }
+            const int e = split_exponent(bound);
+            sc1 = pow2_of(e / 2);
+            sc2 = pow2_of(e - e / 2);
+            if (blockIdx.x == 0 && threadIdx.x == 0) *p.sp.exp = e;
+        }
+    }
+    unsigned amax_bits = 0;
 
     const bool staged = p.list_cap > 0;
     if (!first) {
@@ -222,9 +302,17 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
                 st_vec<T, VEC>(p.y_next + off, yn);
                 if (p.U_out && !first) st_stream<T, VEC>(p.U_out + off, Uv);
                 if (p.graw) st_stream<T, VEC>(p.graw + off, rv);
+                if constexpr (sizeof(T) == 4) {
+                    if (do_split) store_split<VEC>(p.sp, off, yn, sc1, sc2);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) amax_bits = max(amax_bits, __float_as_uint(fabsf(yn.v[v])));
+                }
             }
             cur = nxt;
         }
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (p.sp.amax_out) publish_amax(amax_bits, p.sp.amax_out, sAmax);
     }
     if (p.flags) {
         bad = __reduce_or_sync(0xffffffffu, bad);
@@ -250,6 +338,21 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     const int i = chunk * CH + lane * VEC;
     const bool act_i = i < p.n;
     const bool first = p.first != 0, top = p.top != 0;
+
+    // scale of the fused fp16 split of gAtAy_k:  |gAtAy| <= max_p alpha_p * max|adj(y_{k+1})|
+    float sc1 = 1.f, sc2 = 1.f;
+    bool do_split = false;
+    if constexpr (sizeof(T) == 4) {
+        do_split = p.sp.hi != nullptr && !first;
+        if (do_split) {
+            float amax_alpha = 0.f;
+            for (int q = 0; q < P; ++q) amax_alpha = fmaxf(amax_alpha, fabsf((float)__ldg(p.hyp_k + q * 4)));
+            const int e = split_exponent(amax_alpha * __uint_as_float(__ldg(p.sp.amax_in)));
+            sc1 = pow2_of(e / 2);
+            sc2 = pow2_of(e - e / 2);
+            if (blockIdx.x == 0 && threadIdx.x == 0) *p.sp.exp = e;
+        }
+    }
 
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
@@ -338,7 +441,12 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
             if (!first) {
                 *reinterpret_cast<V*>(tile1 + (size_t)pp * CH * sizeof(T) + lane_bytes) = o_db;
                 if (act_i) {
-                    st_vec<T, VEC>(p.ga + off, o_ga);
+                    if constexpr (sizeof(T) == 4) {
+                        if (do_split) store_split<VEC>(p.sp, off, o_ga, sc1, sc2);
+                        else st_vec<T, VEC>(p.ga + off, o_ga);
+                    } else {
+                        st_vec<T, VEC>(p.ga + off, o_ga);
+                    }
                     st_vec<T, VEC>(p.C + off, o_c);
                     st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
                 }
@@ -403,9 +511,11 @@ __global__ void __launch_bounds__(256) reduce_level_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) seed_adjoint_kernel(const T* __restrict__ Ylast, const T* __restrict__ gYlast,
                                                            const T* __restrict__ label, T coef, int B, int P, int n,
-                                                           T* __restrict__ out) {
+                                                           T* __restrict__ out, unsigned* amax_out) {
     const long long rows = (long long)B * P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __shared__ unsigned sAmax[32];
+    unsigned amax_bits = 0;
     for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
         const long long base = r * n;
         const T* lr = label ? label + (r / P) * n : nullptr;
@@ -413,8 +523,10 @@ __global__ void __launch_bounds__(256) seed_adjoint_kernel(const T* __restrict__
             T v = gYlast ? gYlast[base + i] : (T)0;
             if (lr) v += coef * (Ylast[base + i] - lr[i]);
             out[base + i] = v;
+            amax_bits = max(amax_bits, __float_as_uint(fabsf((float)v)));
         }
     }
+    if (amax_out) publish_amax(amax_bits, amax_out, sAmax);
 }
 
 }  // namespace dadmm

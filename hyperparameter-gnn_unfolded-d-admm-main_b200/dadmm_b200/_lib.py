@@ -16,8 +16,9 @@ LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so
 
 ABI_VERSION = 2
 F32, F64 = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32 = 0, 1, 2
-ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32}
+ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16 = 0, 1, 2, 3
+ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
+         "f16": ALGO_TC_3XF16, "tc_3xf16": ALGO_TC_3XF16}
 FLAG_Y, FLAG_U, FLAG_GRAD, FLAG_YNEXT = 1, 2, 4, 8
 
 
@@ -140,7 +141,7 @@ def launch_count() -> int:
     return int(lib.dadmm_launch_count())
 
 
-PROF_KINDS = ("contract_simt", "contract_tc", "step_fwd", "step_bwd", "reduce_hyp", "loss")
+PROF_KINDS = ("contract_simt", "contract_tc", "step_fwd", "step_bwd", "reduce_hyp", "loss", "split")
 
 
 def profile_enable(on: bool = True):

@@ -45,7 +45,8 @@ enum { DADMM_F32 = 0, DADMM_F64 = 1 };
 enum {
     DADMM_ALGO_AUTO = 0,      /* tcgen05 when the shape allows it (fp32 only), else SIMT          */
     DADMM_ALGO_SIMT = 1,      /* FP32/FP64 FMA pipe, exact IEEE accumulation in k order           */
-    DADMM_ALGO_TC_3XTF32 = 2  /* tcgen05.mma kind::tf32, hi/lo split of both operands (3 MMAs)    */
+    DADMM_ALGO_TC_3XTF32 = 2, /* tcgen05.mma kind::tf32, hi/lo split of both operands (3 MMAs)    */
+    DADMM_ALGO_TC_3XF16 = 3   /* tcgen05.mma kind::f16 on scaled fp16 hi/lo pairs (3 MMAs, 2x tf32 rate) */
 };
 
 /* non-finite bits OR-ed into `flags` by the step kernel (reference guards,
@@ -98,7 +99,7 @@ int64_t dadmm_launch_count(void);
 
 /* Per-kernel-kind timing for bench.py's roofline: after dadmm_profile_enable(1) every launch is bracketed
  * by CUDA events on its stream; dadmm_profile_read sums elapsed ms / launch counts per kind
- * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss; arrays of 8). */
+ * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss, 6 operand split; arrays of 8). */
 int dadmm_profile_enable(int on);
 int dadmm_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
@@ -106,7 +107,8 @@ int dadmm_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
  *   W  (p,i,k) -> W  + p*w_sp + i*w_si + k*w_sk      (i < n_out, k < n_in)
  *   x  (b,p,k) -> x  + b*x_sb + p*x_sp + k*x_sk
  *   out(b,p,i) -> out+ b*o_sb + p*o_sp + i*o_si
- * ws/ws_bytes: scratch for DADMM_ALGO_TC_3XTF32 (see dadmm_contract_ws_bytes), may be NULL for SIMT. */
+ * ws/ws_bytes: scratch for the tensor-core algorithms (dadmm_contract_ws_bytes: the fp16 hi/lo copies of both
+ * operands for DADMM_ALGO_TC_3XF16), may be NULL when that returns 0. */
 int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in,
                    const void* W, int64_t w_sp, int64_t w_si, int64_t w_sk,
                    const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk,
