@@ -388,6 +388,7 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                              cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
+    if (N >= (1ull << 31)) DADMM_FAIL(-1, "unfolded: B*P*n must stay below 2^31 per device (shard the batch)");
     const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;

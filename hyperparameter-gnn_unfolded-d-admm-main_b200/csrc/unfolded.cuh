@@ -55,7 +55,7 @@ __device__ __forceinline__ int split_exponent(float bound) {
 __device__ __forceinline__ float pow2_of(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }
 
 template <int VEC>
-__device__ __forceinline__ void store_split(const SplitOut& sp, size_t off, const Vec<float, VEC>& v, float s1, float s2) {
+__device__ __forceinline__ void store_split(const SplitOut& sp, unsigned off, const Vec<float, VEC>& v, float s1, float s2) {
     __half h[VEC], l[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -73,6 +73,21 @@ __device__ __forceinline__ void store_split(const SplitOut& sp, size_t off, cons
             sp.lo[off + j] = l[j];
         }
     }
+}
+
+// max_p |alpha_p| of one table row, computed by the whole CTA (one load per thread, one barrier) -- a serial
+// P-long load chain per thread cost ~1500 cycles at every CTA start in the first version
+template <typename T>
+__device__ __forceinline__ float block_max_alpha(const T* __restrict__ hyp_row, int P, float* sh /*[32]*/) {
+    float v = 0.f;
+    for (int q = threadIdx.x; q < P; q += blockDim.x) v = fmaxf(v, fabsf((float)__ldg(hyp_row + q * 4)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
+    return m;
 }
 
 // CTA-wide max of per-thread |.| bits -> at most one atomicMax per CTA
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     const bool act_i = i < p.n;
     const bool first = p.first != 0;
     __shared__ unsigned sAmax[32];
+    __shared__ float sAlpha[32];
 
     // scale of the fused fp16 split of y_{k+1} (identical in every CTA)
     float sc1 = 1.f, sc2 = 1.f;
@@ -215,8 +231,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
         if (do_split) {
             float bound = (float)p.V;
             if (p.sp.amax_in) {
-                float amax_alpha = 0.f;
-                for (int q = 0; q < P; ++q) amax_alpha = fmaxf(amax_alpha, fabsf((float)__ldg(p.hyp_k + q * 4)));
+                const float amax_alpha = block_max_alpha(p.hyp_k, P, sAlpha);
                 bound = fminf(bound, __uint_as_float(__ldg(p.sp.amax_in)) + amax_alpha * (float)p.G);
             }
             const int e = split_exponent(bound);
@@ -232,11 +247,11 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
         if (staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
         for (int bl = 0; bl < p.TB; ++bl) {
             const int b = b0 + bl;
-            const T* src = p.y + (size_t)b * P * p.n + i;
+            const T* src = p.y + (((unsigned)b * P) * p.n + i);
             for (int pp = warp; pp < P; pp += nwarps) {
                 V v = vzero<T, VEC>();
-                if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (size_t)pp * p.n);
-                *reinterpret_cast<V*>(S0 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
+                if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+                *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
             }
         }
         __syncthreads();
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         if (b >= p.B) break;
-        const size_t base = (size_t)b * P * p.n + i;
+        const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
         const int node0 = (p.gid ? __ldg(p.gid + b) : 0) * P;
         const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
         auto issue = [&](int pp, Row& L) {
             L.a = L.atb = L.U = L.y = L.d = vzero<T, VEC>();
             if (pp < P && act_i) {
-                const size_t off = base + (size_t)pp * p.n;
+                const unsigned off = base + (unsigned)pp * p.n;
                 L.a = ld_stream<T, VEC>(p.a + off);
                 L.atb = ld_stream<T, VEC>(p.atb + off);
                 L.U = ld_stream<T, VEC>(p.U_in + off);
@@ -269,12 +284,12 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
         issue(warp, cur);
         for (int pp = warp; pp < P; pp += nwarps) {
             issue(pp + nwarps, nxt);
-            const size_t off = base + (size_t)pp * p.n;
+            const unsigned off = base + (unsigned)pp * p.n;
             const T alpha = __ldg(p.hyp_k + pp * 4), tau = __ldg(p.hyp_k + pp * 4 + 1), rho = __ldg(p.hyp_k + pp * 4 + 2);
             const T dg = (T)__ldg(p.deg + node0 + pp);
             V yv = cur.y, dv = cur.d, Uv = cur.U;
             if (!first) {
-                yv = *reinterpret_cast<const V*>(tile + (size_t)pp * CH * sizeof(T) + lane_bytes);
+                yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
                 dv = lap_events<T, VEC>(tile, yv, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
                 const T eta_prev = __ldg(p.hyp_prev + pp * 4 + 3);
 #pragma unroll
@@ -338,6 +353,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     const int i = chunk * CH + lane * VEC;
     const bool act_i = i < p.n;
     const bool first = p.first != 0, top = p.top != 0;
+    __shared__ float sAlpha[32];
 
     // scale of the fused fp16 split of gAtAy_k:  |gAtAy| <= max_p alpha_p * max|adj(y_{k+1})|
     float sc1 = 1.f, sc2 = 1.f;
@@ -345,8 +361,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     if constexpr (sizeof(T) == 4) {
         do_split = p.sp.hi != nullptr && !first;
         if (do_split) {
-            float amax_alpha = 0.f;
-            for (int q = 0; q < P; ++q) amax_alpha = fmaxf(amax_alpha, fabsf((float)__ldg(p.hyp_k + q * 4)));
+            const float amax_alpha = block_max_alpha(p.hyp_k, P, sAlpha);
             const int e = split_exponent(amax_alpha * __uint_as_float(__ldg(p.sp.amax_in)));
             sc1 = pow2_of(e / 2);
             sc2 = pow2_of(e - e / 2);
@@ -358,12 +373,12 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
-        const T* src = p.y + (size_t)b * P * p.n + i;
+        const T* src = p.y + (((unsigned)b * P) * p.n + i);
         for (int pp = warp; pp < P; pp += nwarps) {
             V v = vzero<T, VEC>();
-            if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (size_t)pp * p.n);
-            *reinterpret_cast<V*>(S0 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
-            if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + ((size_t)(bl * P + pp) * CH) * sizeof(T) + lane_bytes) = v;
+            if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+            *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
+            if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
         }
     }
     __syncthreads();
@@ -372,17 +387,17 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         if (b >= p.B) break;
-        const size_t base = (size_t)b * P * p.n + i;
+        const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
         const int node0 = (p.gid ? __ldg(p.gid + b) : 0) * P;
         const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
         unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
-        const T* lab = p.label ? p.label + (size_t)b * p.n + i : nullptr;
+        const T* lab = p.label ? p.label + ((unsigned)b * p.n + i) : nullptr;
         auto issue = [&](int pp, Row& L) {
             L.t = L.c = L.r = L.u = L.d = L.g = vzero<T, VEC>();
             if (pp < P && act_i) {
-                const size_t off = base + (size_t)pp * p.n;
+                const unsigned off = base + (unsigned)pp * p.n;
                 L.t = ld_vec<T, VEC>(p.Tb + off);
                 L.r = ld_stream<T, VEC>(p.graw + off);
                 if (first) {
@@ -400,10 +415,10 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
         issue(warp, cur);
         for (int pp = warp; pp < P; pp += nwarps) {
             issue(pp + nwarps, nxt);
-            const size_t off = base + (size_t)pp * p.n;
+            const unsigned off = base + (unsigned)pp * p.n;
             const T alpha = __ldg(p.hyp_k + pp * 4), rho = __ldg(p.hyp_k + pp * 4 + 2);
             const T dg = (T)__ldg(p.deg + node0 + pp);
-            const V yv = *reinterpret_cast<const V*>(tile + (size_t)pp * CH * sizeof(T) + lane_bytes);
+            const V yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
             V draw = cur.d;
             T eta_prev = (T)0;
             if (!first) {
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
                 }
             }
             if (!first) {
-                *reinterpret_cast<V*>(tile1 + (size_t)pp * CH * sizeof(T) + lane_bytes) = o_db;
+                *reinterpret_cast<V*>(tile1 + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes) = o_db;
                 if (act_i) {
                     if constexpr (sizeof(T) == 4) {
                         if (do_split) store_split<VEC>(p.sp, off, o_ga, sc1, sc2);
@@ -452,7 +467,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
                 }
             }
             const T s = warp_sum4(pa, pt, pr, pe, lane);
-            if ((lane & 7) == 0) p.partials[(((size_t)chunk * p.B + b) * P + pp) * 4 + (lane >> 3)] = s;
+            if ((lane & 7) == 0) p.partials[(((unsigned)chunk * p.B + b) * P + pp) * 4 + (lane >> 3)] = s;
             cur = nxt;
         }
     }
@@ -461,15 +476,15 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         if (b >= p.B) break;
-        const size_t base = (size_t)b * P * p.n + i;
+        const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
         const unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
         for (int pp = warp; pp < P; pp += nwarps) {
-            const V xq = *reinterpret_cast<const V*>(tile1 + (size_t)pp * CH * sizeof(T) + lane_bytes);
+            const V xq = *reinterpret_cast<const V*>(tile1 + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
             const V lt = lap_adj<T, VEC>(tile1, xq, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
             if (act_i) {
-                const size_t off = base + (size_t)pp * p.n;
+                const unsigned off = base + (unsigned)pp * p.n;
                 V s = ld_vec<T, VEC>(p.Tb + off);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) s.v[v] += lt.v[v];
