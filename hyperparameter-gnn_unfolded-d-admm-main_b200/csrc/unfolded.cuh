@@ -196,11 +196,17 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
     return k;
 }
 
+#ifndef DADMM_LEVEL_BWD_PREFETCH
+#define DADMM_LEVEL_BWD_PREFETCH 0   // register double-buffering of the next row: 2.24 ms with, 1.78 ms without (B200, cfg4)
+#endif
+#ifndef DADMM_LEVEL_FWD_PREFETCH
+#define DADMM_LEVEL_FWD_PREFETCH 0   // same finding as for the backward kernel: occupancy beats register double-buffering
+#endif
 #ifndef DADMM_LEVEL_MINB_FWD
-#define DADMM_LEVEL_MINB_FWD 4      // round-1 sweep on B200 (cfg4): 1 -> 1.34 ms, 3 -> 1.28, 4 -> 1.17 per level
+#define DADMM_LEVEL_MINB_FWD 5      // round-1 sweep on B200 (cfg4, no prefetch): 3 -> 1.51 ms, 4 -> 1.31, 5 -> 1.24 per level
 #endif
 #ifndef DADMM_LEVEL_MINB_BWD
-#define DADMM_LEVEL_MINB_BWD 3      // 1 -> 2.45 ms, 2 -> 2.34, 3 -> 2.29, 4 -> 2.76 (spills)
+#define DADMM_LEVEL_MINB_BWD 3      // no prefetch: 3 -> 1.78 ms (80 regs, no spills), 4 -> 2.10 (spills)
 #endif
 
 template <typename T, int VEC>
@@ -281,9 +287,15 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
             }
         };
         Row cur, nxt;
+#if DADMM_LEVEL_FWD_PREFETCH
         issue(warp, cur);
+#endif
         for (int pp = warp; pp < P; pp += nwarps) {
+#if DADMM_LEVEL_FWD_PREFETCH
             issue(pp + nwarps, nxt);
+#else
+            issue(pp, cur);
+#endif
             const unsigned off = base + (unsigned)pp * p.n;
             const T alpha = __ldg(p.hyp_k + pp * 4), tau = __ldg(p.hyp_k + pp * 4 + 1), rho = __ldg(p.hyp_k + pp * 4 + 2);
             const T dg = (T)__ldg(p.deg + node0 + pp);
@@ -323,7 +335,9 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
                     for (int v = 0; v < VEC; ++v) amax_bits = max(amax_bits, __float_as_uint(fabsf(yn.v[v])));
                 }
             }
+#if DADMM_LEVEL_FWD_PREFETCH
             cur = nxt;
+#endif
         }
     }
     if constexpr (sizeof(T) == 4) {
@@ -412,9 +426,15 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
         V labv = vzero<T, VEC>();
         if (lab && act_i) labv = ld_vec<T, VEC>(lab);
         Row cur, nxt;
+#if DADMM_LEVEL_BWD_PREFETCH
         issue(warp, cur);
+#endif
         for (int pp = warp; pp < P; pp += nwarps) {
+#if DADMM_LEVEL_BWD_PREFETCH
             issue(pp + nwarps, nxt);
+#else
+            issue(pp, cur);
+#endif
             const unsigned off = base + (unsigned)pp * p.n;
             const T alpha = __ldg(p.hyp_k + pp * 4), rho = __ldg(p.hyp_k + pp * 4 + 2);
             const T dg = (T)__ldg(p.deg + node0 + pp);
@@ -468,7 +488,9 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
             }
             const T s = warp_sum4(pa, pt, pr, pe, lane);
             if ((lane & 7) == 0) p.partials[(((unsigned)chunk * p.B + b) * P + pp) * 4 + (lane >> 3)] = s;
+#if DADMM_LEVEL_BWD_PREFETCH
             cur = nxt;
+#endif
         }
     }
     if (first) return;

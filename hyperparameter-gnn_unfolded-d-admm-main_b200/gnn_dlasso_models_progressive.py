@@ -142,7 +142,8 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
             Wt = W.transpose(1, 2).contiguous()
             if torch.equal(W, Wt):
                 Wt = W
-            self._ops[key] = (A, W, Wt)
+            At = A[0].transpose(1, 2).contiguous()      # [P,n,m]: K-major operator for Atb on the tensor-core path
+            self._ops[key] = (A, W, Wt, At)
         return self._ops[key]
 
     @property
@@ -171,8 +172,8 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         K = training_iterations if training_iterations is not None else self.K
         DF.require_cuda(b)
         device, B = b.device, len(b)
-        A, W, Wt = self._operators(device)
-        Atb = DF.atx(A, b.to(W.dtype))                                     # [B,P,n,1]
+        A, W, Wt, At = self._operators(device)
+        Atb = DF.contract(At, b.to(W.dtype).squeeze(-1), algo=self.contract_algo).unsqueeze(-1)   # [B,P,n,1]
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         adj_hat = normalized_adjacency(graph_list, self.P, device, W.dtype)
         y0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2

@@ -74,7 +74,8 @@ class DLASSO_unfolded(nn.Module):
             Wt = W.transpose(1, 2).contiguous()
             if torch.equal(W, Wt):
                 Wt = W
-            self._ops[key] = (A, W, Wt)
+            At = A[0].transpose(1, 2).contiguous()      # [P,n,m]: K-major operator for Atb on the tensor-core path
+            self._ops[key] = (A, W, Wt, At)
         return self._ops[key]
 
     @property
@@ -91,8 +92,8 @@ class DLASSO_unfolded(nn.Module):
         batch_size, device = len(b), b.device
         K = self.K if K is None else min(K, self.K)
         DF.require_cuda(b)
-        A, W, Wt = self._operators(device)
-        Atb = DF.atx(A, b.to(W.dtype)).squeeze(-1)
+        A, W, Wt, At = self._operators(device)
+        Atb = DF.contract(At, b.to(W.dtype).squeeze(-1), algo=self.contract_algo)          # A_p^T b_p  (reference :45)
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         # initial noise: same three draws, same order / shape / device as the reference (:49-51)
         y0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
