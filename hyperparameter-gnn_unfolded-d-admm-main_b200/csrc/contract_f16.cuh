@@ -176,12 +176,20 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t lead = full_bar(stage) & 0xFEFFFFFFu;     // same offset in the pair's leader CTA
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);
                     const uint32_t sb = stage_base(stage);
+#if defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT == 2
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), STAGE);      // timing experiment: W tiles only
+                    tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
+                    tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
+#elif defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT == 3
+                    if (rank == 0) mbar_arrive(full_bar(stage));                // timing experiment: no TMA at all
+#else
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);
                     tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
                     tma_load_3d_pair(sb + TILE, &map_xh, lead, kb * BKE, ag, b0);
                     tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
                     tma_load_3d_pair(sb + 3 * TILE, &map_xl, lead, kb * BKE, ag, b0);
+#endif
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }

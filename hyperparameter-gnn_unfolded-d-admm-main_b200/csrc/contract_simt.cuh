@@ -187,16 +187,27 @@ template <>
 struct SimtCfg<double> {
     static constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 };
+// small batches (the reference's default B = 16..64): a 128-wide batch tile would idle 75 % of the CTA and leave
+// most SMs without work, so use 64 x 32 tiles / 128 threads
+template <typename T>
+struct SimtCfgSmall {
+    static constexpr int BM = 64, BN = 32, BK = 16, TM = 4, TN = 4;
+};
 
-template <typename T, int WMODE, int XMODE>
-int launch_contract_simt_modes(const GemmParams<T>& p, cudaStream_t s) {
-    using C = SimtCfg<T>;
+template <typename T, typename C, int WMODE, int XMODE>
+int launch_contract_simt_cfg(const GemmParams<T>& p, cudaStream_t s) {
     dim3 grid(ceil_div(p.M, C::BM), ceil_div(p.B, C::BN), p.P);
     ProfScope prof(PROF_CONTRACT_SIMT, s);
     contract_simt_kernel<T, C::BM, C::BN, C::BK, C::TM, C::TN, WMODE, XMODE>
         <<<grid, (C::BM / C::TM) * (C::BN / C::TN), 0, s>>>(p);
     DADMM_LAUNCHED();
     return 0;
+}
+
+template <typename T, int WMODE, int XMODE>
+int launch_contract_simt_modes(const GemmParams<T>& p, cudaStream_t s) {
+    if (p.B <= 64) return launch_contract_simt_cfg<T, SimtCfgSmall<T>, WMODE, XMODE>(p, s);
+    return launch_contract_simt_cfg<T, SimtCfg<T>, WMODE, XMODE>(p, s);
 }
 
 template <typename T>

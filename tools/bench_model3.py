@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Model #3 (GNN hypernetwork between iterations), BASELINE configs[1] shapes: P=5, n=500, m=100, batch 1024, K iterations.
+    python tools/bench_model3.py [--K 15] [--batch 1024] [--hidden 100]"""
+import argparse, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench, torch
+ap = argparse.ArgumentParser()
+ap.add_argument("--K", type=int, default=15); ap.add_argument("--batch", type=int, default=1024); ap.add_argument("--hidden", type=int, default=100)
+ap.add_argument("--steps", type=int, default=3)
+o = ap.parse_args()
+import gnn_dlasso_models_progressive as M, gnn_dlasso_utils
+from dadmm_b200 import _lib
+w = dict(P=5, n=500, m=100, K=o.K, B=o.batch, graph_prob=0.5)
+dev = torch.device("cuda:0")
+args, A, label, graphs, _ = bench.make_problem(w, o.batch)
+args.GHyp_hidden = o.hidden
+label = label.to(dev)
+b = torch.stack([A[0, p].to(dev) @ label for p in range(w["P"])], dim=1).contiguous()
+torch.manual_seed(0)
+model = M.DLASSO_GNNHyp3_Progressive(A, args).to(dev)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+def step():
+    Y, hyp = model(b, graphs, training_iterations=o.K)
+    lm, lf = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False)
+    opt.zero_grad(); lf.backward(); torch.nn.utils.clip_grad_norm_(model.parameters(), 100.0); opt.step()
+    return lf
+for _ in range(2): step()
+torch.cuda.synchronize(); n0 = _lib.launch_count(); t0 = time.perf_counter()
+for _ in range(o.steps): lf = step()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / o.steps
+print(f"model3 P=5 n=500 B={o.batch} K={o.K} hidden={o.hidden}: {1e3*t:.1f} ms/step, {o.K*o.batch/t:.0f} iter*problems/s, "
+      f"loss_final={float(lf.detach()):.5f}, dadmm kernels/step={(_lib.launch_count()-n0)//o.steps}")
