@@ -43,6 +43,8 @@ WORKLOADS = {
                  desc="BASELINE configs[2]: P=20, n=256, m=64, K=25, batch 4096, ER p=0.5, fresh graph per problem"),
     "cfg1": dict(P=5, n=500, m=100, K=15, B=32, graph_prob=0.5, B_ref=32,
                  desc="BASELINE configs[0]: P=5, n=500, m=100, K=15, batch 32, one shared ER p=0.5 graph"),
+    "cfg5": dict(P=100, n=2048, m=512, K=50, B=2048, graph_prob=0.1, B_ref=1,
+                 desc="BASELINE configs[4] per-GPU shard: P=100, n=2048, m=512, K=50, batch 2048 (16384 over 8 GPUs), ER p=0.1 bridged; inference"),
     "tiny": dict(P=5, n=64, m=16, K=4, B=16, graph_prob=0.5, B_ref=4, desc="smoke-sized"),
 }
 
@@ -92,7 +94,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -100,15 +102,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: samples taken before this are dropped."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t1 = time.time()
+        time.sleep(0.12)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if getattr(self, "t0", 0) <= t <= t1 + 0.06]
+        if not rows:                      # timed region shorter than one sampling period: keep the closest sample
+            rows = [r for _, r in self.rows[-1:]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -224,9 +234,11 @@ def run_ours(opt, w):
     # ---- device-resident timing (value) ------------------------------------------------------------------
     for _ in range(max(opt.warmup, 3)):
         step(b_dev, label_dev)
-    barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    sampler.start()                       # nvidia-smi needs ~100 ms to emit its first line: start it before the last warm-up
+    step(b_dev, label_dev)
+    barrier()
+    sampler.mark()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -328,6 +340,14 @@ def make_roofline(w, B_loc, prof, t_step_ms):
         roof = {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
                 "share_of_step": ms / t_step_ms}
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (same workload / batch)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("B") == B_loc and tj.get("P") == P and tj.get("n") == n:
+            roof["traffic"] = tj["dram_bytes_per_launch"].get("contract_tc" if kind.startswith("contract") else kind)
+            roof["traffic_source"] = tj["source"]
+    except Exception:
+        pass
     # secondary: HBM fraction of the streaming kernels, always reported
     for k2, per_elem in (("step_fwd", 20), ("step_bwd", 36)):
         if prof[k2][1]:

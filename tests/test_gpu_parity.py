@@ -333,12 +333,13 @@ def test_contract_tc_vs_fp64(B, P, n, algo):
     assert torch.equal(DF.contract(Wd, xd, algo=algo), o_tc)      # deterministic
 
 
+@pytest.mark.parametrize("n", [256, 260])        # 256: fused fp16 operand splits; 260 (n % 8 != 0): per-call split pass
 @pytest.mark.parametrize("a_scale", [0.1, 1.0])
-def test_unfolded_tc_vs_simt_vs_fp64_oracle(a_scale):
+def test_unfolded_tc_vs_simt_vs_fp64_oracle(a_scale, n):
     """K-step trajectories with the tcgen05 contraction against the fp64 oracle, next to the exact-FMA path:
     the tensor-core path must stay within max(1e-5, 2x) of the FMA path's own distance to fp64."""
     DF, BG = _df()
-    P, n, m, K, B = 4, 256, 64, 8, 256            # n > 128 so that the CTA-pair kernels (256-row tiles) are exercised
+    P, m, K, B = 4, 64, 8, 256                    # n > 128 so that the CTA-pair kernels (256-row tiles) are exercised
     pr = random_problem(P, n, m, B, K, seed=21, a_scale=a_scale)
     hyp = O.hyp_table(pr["param"], torch.tensor([0.1, 0.99, 0.99, 0.99]), True)
     A64 = pr["A"].double()

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--inference", action="store_true", help="forward only under no_grad (config-5 style sweep)")
     o = ap.parse_args()
     import unfolded_DLASSO
     import gnn_dlasso_utils
@@ -36,13 +37,23 @@ def main():
     model.contract_algo = o.algo
     with torch.no_grad():
         model.seq_hyp.param.copy_(param)
-    for _ in range(o.steps):
-        Y, _ = model(b, graphs)
-        lm, lf = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False)
-        model.zero_grad()
-        lf.backward()
+    import time
+    for it in range(o.steps + 1):
+        if it == 1:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        if o.inference:
+            with torch.no_grad():
+                Y, _ = model(b, graphs)
+                lm, lf = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False)
+        else:
+            Y, _ = model(b, graphs)
+            lm, lf = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False)
+            model.zero_grad()
+            lf.backward()
     torch.cuda.synchronize()
-    print("ok", float(lf.detach()))
+    dt = (time.perf_counter() - t0) / max(o.steps, 1)
+    print("ok", float(lf.detach()), f"{1e3*dt:.2f} ms/step", f"{o.K*B/dt:.0f} iter*problems/s", f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
 
 
 if __name__ == "__main__":
