@@ -115,6 +115,7 @@ struct Params {
     int m_tiles, n_tiles, k_blocks, total_tiles;
     const int *exp_w, *exp_x;      // device: scale exponents of the two operands
     unsigned* amax_out;            // device, optional: running max |out| bits (feeds the next operand split's bound)
+    const float* sub;              // device, optional [B,P,n_out] laid out like `out`: out = W x - sub (the Atb term)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -240,32 +241,37 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             float acc[COLS_PER_THREAD];
             const int i = i0 + q * 32 + lane;
             float* orow = p.out + (long long)ag * p.n_out + i;
-            if (p.accumulate) {
-                // out += W x: seed the accumulators with the old values in the SCALED domain (power-of-two factors,
-                // exact); the loads fly while the tensor core works on the first chunk
+            const bool seeded = p.accumulate || p.sub != nullptr;
+            if (seeded) {
+                // out += W x  /  out = W x - sub: the accumulators start from the old values (or -sub).  Only the raw
+                // loads are issued here -- 128 independent LDGs per thread that fly while the tensor core works on the
+                // first chunk; the (exact, power-of-two) move into the scaled domain is folded into the first
+                // accumulation below.  (With the scaling attached to each load, ptxas serialised the loads in small
+                // scoreboard batches: +0.7 ms per launch, round-1 measurement.)
+                const float* srow = p.accumulate ? orow : p.sub + (long long)ag * p.n_out + i;
 #pragma unroll
                 for (int c = 0; c < COLS_PER_THREAD; ++c) {
                     const int b = b0 + c;
-                    acc[c] = (i < p.n_out && b < p.B) ? __ldcs(orow + (long long)b * p.o_sb) * rescale * rescale2 : 0.0f;
+                    acc[c] = (i < p.n_out && b < p.B) ? __ldcs(srow + (long long)b * p.o_sb) : 0.0f;
                 }
             }
+            const float seed1 = p.accumulate ? rescale : -rescale;
             for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
                 const int buf = ci & 1;
                 mbar_wait(tfull_bar(buf), (uint32_t)(ci >> 1) & 1u);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * COLS_PER_THREAD);
-                const bool seed = (ch == 0) && !p.accumulate;
-#if defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT >= 1
-                if (p.n_in < 0 || ch == 0)   // timing experiment: drain only the first chunk
-#endif
 #pragma unroll
                 for (int j = 0; j < COLS_PER_THREAD / 32; ++j) {
                     uint32_t v[32];
                     tmem_ld32(taddr + 32u * j, v);
                     tmem_ld_wait();
-                    if (seed) {
+                    if (ch == 0 && !seeded) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) acc[32 * j + c] = __uint_as_float(v[c]);
+                    } else if (ch == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[32 * j + c] = (acc[32 * j + c] * seed1) * rescale2 + __uint_as_float(v[c]);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) acc[32 * j + c] += __uint_as_float(v[c]);
@@ -360,7 +366,7 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 // out[b,p,:] (+)= W_p x[b,p,:] from prepared operands: wprep = split of W viewed as [P*n_out][n_in],
 // xprep = split of x viewed as [B*P][n_in]
 inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
-                  cudaStream_t s, unsigned* amax_out = nullptr) {
+                  cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr) {
     tc::EncodeTiledFn enc = tc::encode_fn();
     if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
     const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
@@ -377,7 +383,7 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     p.n_tiles = ceil_div(B, 256);
     p.k_blocks = ceil_div(n_in, BKE);
     p.total_tiles = P * p.m_tiles * p.n_tiles;
-    p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out;
+    p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub;
     static int num_sms = [] {
         int dev = 0, n = 148;
         cudaGetDevice(&dev);

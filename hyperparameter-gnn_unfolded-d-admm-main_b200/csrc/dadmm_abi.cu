@@ -331,9 +331,10 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, int top, const void* y,
                           const void* U_prev, const void* d0, const void* graw, void* Tb, void* C, void* ga,
                           const void* gY_prev, const void* label, double coef_prev, void* partials, const SplitOut& sp,
-                          cudaStream_t s) {
+                          int graw_is_residual, cudaStream_t s) {
     LevelBwdParams<T> p;
     p.sp = sp;
+    p.graw_is_residual = graw_is_residual;
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr); p.top = top;
     p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx; p.deg = g->deg; p.gid = g->graph_id;
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
@@ -413,16 +414,20 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         const char* Uin = (k <= 1) ? (const char*)U0 : Uslot(k - 1);
         char* Uout = (k == 0 || k == K - 1) ? nullptr : Uslot(k);   // U_{K-1} is consumed in-register only
         SplitOut sp{};
+        // fused path: the contraction epilogue subtracts Atb and writes a_k' = AtA y_k - Atb straight into the saved
+        // stream (R_save[k]) -- the forward level neither reads Atb nor writes r_k; the backward rebuilds r_k from a_k'
+        char* ak = (fused && R_save) ? (char*)R_save + (size_t)k * NB : a;
         if (fused) {
-            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)a, sPn, 0, s)) return e;
+            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)ak, sPn, 0, s, nullptr, (const float*)Atb)) return e;
             if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
         } else {
             if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, w8, cw, s, k > 0))
                 return e;
         }
         if (int e = level_fwd_impl<T>(dtype, B, P, n, graph, clamps + k, k ? clamps + k - 1 : nullptr, (const char*)hyp + k * row,
-                                      k ? (const char*)hyp + (k - 1) * row : nullptr, yk, Uin, d0, a, Atb,
-                                      (char*)Y + (size_t)k * NB, Uout, R_save ? (char*)R_save + (size_t)k * NB : nullptr,
+                                      k ? (const char*)hyp + (k - 1) * row : nullptr, yk, Uin, d0, ak, fused ? nullptr : Atb,
+                                      (char*)Y + (size_t)k * NB, Uout,
+                                      (R_save && !fused) ? (char*)R_save + (size_t)k * NB : nullptr,
                                       flags ? flags + k : nullptr, sp, s))
             return e;
     }
@@ -476,7 +481,7 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                                       k ? (const char*)hyp + (k - 1) * row : nullptr, k == K - 1, yk, Uprev, d0,
                                       (const char*)R_save + (size_t)k * NB, Tb, C, ga,
                                       (gY && k) ? (const char*)gY + (size_t)(k - 1) * NB : nullptr, label,
-                                      (with_loss && k) ? loss_coef[k - 1] : 0.0, part, sp, s))
+                                      (with_loss && k) ? loss_coef[k - 1] : 0.0, part, sp, fused ? 1 : 0, s))
             return e;
         {
             ProfScope prof(PROF_REDUCE_HYP, s);

@@ -124,6 +124,7 @@ struct LevelBwdParams {
     T G, V, D, Uc_prev;
     int hasD;
     const T *y, *U_prev, *d0, *graw;
+    int graw_is_residual;               // 1: `graw` holds AtA y - Atb and r_k is rebuilt here (no saved r_k stream)
     T *Tb, *C, *ga;
     const T *gY_prev, *label;
     T coef_prev;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
             if (pp < P && act_i) {
                 const unsigned off = base + (unsigned)pp * p.n;
                 L.a = ld_stream<T, VEC>(p.a + off);
-                L.atb = ld_stream<T, VEC>(p.atb + off);
+                if (p.atb) L.atb = ld_stream<T, VEC>(p.atb + off);
                 L.U = ld_stream<T, VEC>(p.U_in + off);
                 if (first) {
                     L.y = ld_vec<T, VEC>(p.y + off);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const T y = yv.v[v], U = Uv.v[v];
-                T rr = sub_rn(cur.a.v[v], cur.atb.v[v]);
+                T rr = p.atb ? sub_rn(cur.a.v[v], cur.atb.v[v]) : cur.a.v[v];     // a already holds AtA y - Atb in the fused path
                 rr = add_rn(rr, mul_rn(sign_of(y), tau));
                 rr = add_rn(rr, mul_rn(U, dg));
                 rr = add_rn(rr, mul_rn(dv.v[v], rho));
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
                 L.r = ld_stream<T, VEC>(p.graw + off);
                 if (first) {
                     L.d = ld_stream<T, VEC>(p.d0 + off);
+                    if (p.graw_is_residual) L.u = ld_stream<T, VEC>(p.U_prev + off);      // U_0
                 } else {
                     if (!top) L.c = ld_vec<T, VEC>(p.C + off);
                     L.u = ld_stream<T, VEC>(p.U_prev + off);
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
 #endif
             const unsigned off = base + (unsigned)pp * p.n;
             const T alpha = __ldg(p.hyp_k + pp * 4), rho = __ldg(p.hyp_k + pp * 4 + 2);
+            const T tau = p.graw_is_residual ? __ldg(p.hyp_k + pp * 4 + 1) : (T)0;
             const T dg = (T)__ldg(p.deg + node0 + pp);
             const V yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
             V draw = cur.d;
@@ -449,9 +452,17 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
             T pa = (T)0, pt = (T)0, pr = (T)0, pe = (T)0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const T y = yv.v[v], rr = cur.r.v[v];
+                const T y = yv.v[v];
                 const bool mD = (first || !p.hasD) ? true : in_closed(draw.v[v], p.D);
                 const T d = (first || !p.hasD) ? draw.v[v] : clamp_sym(draw.v[v], p.D);
+                T rr = cur.r.v[v];
+                if (p.graw_is_residual) {
+                    // r_k = (AtA y - Atb) + sign(y) tau + U_k deg + d_k rho with U_k = clamp(U_{k-1} + d_k eta_{k-1})
+                    const T Uk = first ? cur.u.v[v] : clamp_sym(add_rn(cur.u.v[v], mul_rn(d, eta_prev)), p.Uc_prev);
+                    rr = add_rn(rr, mul_rn(sign_of(y), tau));
+                    rr = add_rn(rr, mul_rn(Uk, dg));
+                    rr = add_rn(rr, mul_rn(d, rho));
+                }
                 const T g = clamp_sym(rr, p.G);
                 const T z = sub_rn(y, mul_rn(alpha, g));
                 const T zb = in_closed(z, p.V) ? cur.t.v[v] : (T)0;

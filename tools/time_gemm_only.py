@@ -6,10 +6,11 @@ sys.path.insert(0, os.path.join(ROOT, "hyperparameter-gnn_unfolded-d-admm-main_b
 import torch
 from dadmm_b200 import functional as DF, _lib
 algo = sys.argv[1] if len(sys.argv) > 1 else "f16"
+acc = len(sys.argv) > 2 and sys.argv[2] == "acc"
 B, P, n = 4096, 50, 1024
 W = torch.randn(P, n, n, device="cuda"); x = torch.randn(B, P, n, device="cuda"); out = torch.empty_like(x)
-for _ in range(3): DF.contract(W, x, out=out, algo=algo)
+for _ in range(3): DF.contract(W, x, out=out, algo=algo, accumulate=acc)
 torch.cuda.synchronize(); _lib.profile_enable(True)
-for _ in range(10): DF.contract(W, x, out=out, algo=algo)
+for _ in range(10): DF.contract(W, x, out=out, algo=algo, accumulate=acc)
 torch.cuda.synchronize(); pr = _lib.profile_read(); _lib.profile_enable(False)
-print(algo, {k: round(v[0] / max(v[1], 1), 3) for k, v in pr.items() if v[1]})
+print(algo, 'accumulate' if acc else 'plain', {k: round(v[0] / max(v[1], 1), 3) for k, v in pr.items() if v[1]})
