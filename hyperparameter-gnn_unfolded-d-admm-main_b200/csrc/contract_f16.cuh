@@ -22,16 +22,23 @@
 namespace dadmm {
 namespace f16 {
 
-using tc::A_BYTES;   // 128 rows x 64 bytes
+#ifndef DADMM_F16_BK64
+#define DADMM_F16_BK64 1        // round-1 sweep: 64-k blocks (SWIZZLE_128B, 3 stages) 1.05 ms vs 32-k blocks (SWIZZLE_64B, 6 stages) 1.12 ms
+#endif
+#if DADMM_F16_BK64
+constexpr int BKE = 64;                          // k elements per k-block (128-byte fp16 rows, SWIZZLE_128B)
+constexpr int STAGES = 3;
+#else
 constexpr int BKE = 32;                          // k elements per k-block (64-byte fp16 rows, SWIZZLE_64B)
 constexpr int STAGES = 6;
-constexpr int TILE = A_BYTES;                    // every operand tile: 128 rows x 64 B = 8 KB
+#endif
+constexpr int TILE = 128 * BKE * 2;              // every operand tile: 128 rows x (64 | 128) B
 constexpr int STAGE = 4 * TILE;                  // A_hi | B_hi | A_lo | B_lo
 constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 constexpr int THREADS = 384;                     // warps 0-3: TMA, MMA, (2 idle); warps 4-11: accumulate + store
 constexpr int EPI_WARP0 = 4;
 #ifndef DADMM_F16_KB_PER_CHUNK
-#define DADMM_F16_KB_PER_CHUNK 2
+#define DADMM_F16_KB_PER_CHUNK (DADMM_F16_BK64 ? 1 : 2)
 #endif
 constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;   // 2 x 32 = 64 k per tensor-core partial sum
 constexpr int COLS_PER_THREAD = 128;
@@ -97,6 +104,15 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// K-major shared-memory matrix descriptor for this kernel's tile geometry
+__device__ __forceinline__ uint64_t tile_desc(uint32_t saddr) {
+#if DADMM_F16_BK64
+    // SWIZZLE_128B: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+#else
+    return tc::umma_desc(saddr);
+#endif
 }
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
@@ -213,8 +229,8 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
 #pragma unroll
                         for (int ks = 0; ks < BKE / 16; ++ks) {
                             const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the 64-byte swizzled row
-                            const uint64_t da = umma_desc(sa + koff), db = umma_desc(sb + koff);
-                            const uint64_t da_lo = umma_desc(sa_lo + koff), db_lo = umma_desc(sb_lo + koff);
+                            const uint64_t da = tile_desc(sa + koff), db = tile_desc(sb + koff);
+                            const uint64_t da_lo = tile_desc(sa_lo + koff), db_lo = tile_desc(sb_lo + koff);
                             umma_f16_pair(d_tmem, da_lo, db, (kb != ch * KB_PER_CHUNK) || ks != 0);
                             umma_f16_pair(d_tmem, da, db_lo, 1u);
                             umma_f16_pair(d_tmem, da, db, 1u);
@@ -351,14 +367,15 @@ inline int split_tensor(const float* x, long long rows, int n, long long ld, voi
     return 0;
 }
 
-inline bool dims_supported(int B, int P, int n_out, int n_in) { return B >= 128 && n_out > 128 && n_in >= 32 && P >= 1; }
+inline bool dims_supported(int B, int P, int n_out, int n_in) { return B >= 128 && n_out > 128 && n_in >= BKE && P >= 1; }
 
 inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
                    cuuint64_t s1, cuuint64_t s2, cuuint32_t b0, cuuint32_t b1, cuuint32_t b2) {
     cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {s1, s2};
     cuuint32_t box[3] = {b0, b1, b2}, es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     DADMM_F16_BK64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DADMM_FAIL(-4, "cuTensorMapEncodeTiled(f16) failed: %d", (int)r);
     return 0;
 }
