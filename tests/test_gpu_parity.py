@@ -401,3 +401,45 @@ def test_fused_levels_equal_chain_of_single_steps(name):
     (Y2 * gY).sum().backward()
     assert torch.equal(Y1, Y2)
     assert rel_l2(h1.grad.cpu(), h2.grad.cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def _edge_graph(P, kind, seed):
+    import networkx as nx
+    if kind == "er":
+        return nx.erdos_renyi_graph(P, 0.5, seed=seed)
+    g = nx.Graph()
+    g.add_nodes_from(range(P))
+    if kind == "odd" and P >= 3:          # a self-loop, an isolated node (P-1), a path
+        g.add_edges_from([(0, 1), (1, 1)] + [(i, i + 1) for i in range(1, P - 2)])
+    return g                               # "empty": no edges at all
+
+
+@pytest.mark.parametrize("B,P,n,K,kind", [(1, 1, 4, 1, "empty"), (3, 2, 6, 2, "er"), (2, 9, 10, 3, "odd"),
+                                          (130, 3, 264, 3, "er"), (5, 70, 8, 2, "er"), (3, 150, 8, 2, "er")])
+def test_edge_shapes_match_oracle(B, P, n, K, kind):
+    """Degenerate / ragged shapes through the default path: single agent without neighbours, K = 1 and 2, isolated
+    nodes and self-loops, P larger than one warp-pass of the tile, dense P=150 graphs whose neighbour lists do not
+    fit in shared memory (global-memory list path), a batch that exercises the fp16 tensor-core path
+    with ragged 256-row / 256-column tiles."""
+    DF, BG = _df()
+    gen = torch.Generator().manual_seed(B * 100 + P)
+    m = max(2, n // 2)
+    A = torch.randn((1, P, m, n), generator=gen) * 0.3
+    b = torch.randn((B, P, m, 1), generator=gen)
+    graphs = [_edge_graph(P, kind, seed=i) for i in range(B)]
+    y0, U0, d0 = (torch.randn((B, P, n, 1), generator=gen) * 1e-2 for _ in range(3))
+    hyp = O.hyp_table(torch.randn((K, P, 4), generator=gen) * 0.3, torch.tensor([0.1, 0.99, 0.99, 0.99]), True).requires_grad_(True)
+    gYr = torch.randn((K, B, P, n, 1), generator=gen)
+    A64 = A.double()
+    h64 = hyp.detach().double().requires_grad_(True)
+    Y64 = O.unfolded_forward(O.atx(A64, A64), O.atx(A64, b.double()), graphs, y0.double(), U0.double(), d0.double(), h64)
+    (Y64 * gYr.double()).sum().backward()
+    Ad = A.to(DEV)
+    W = DF.atx(Ad, Ad)[0].contiguous()
+    hd = hyp.detach().to(DEV).requires_grad_(True)
+    Y = DF.Unfolded.apply(hd, W, W.transpose(1, 2).contiguous(), DF.atx(Ad, b.to(DEV)).squeeze(-1), _dev(y0), _dev(U0), _dev(d0),
+                          BG.from_graph_list(graphs, P, DEV), [DF.clamps_model1(k) for k in range(K)], "auto", None, None)
+    (Y * gYr.to(DEV)).sum().backward()
+    assert rel_l2(Y.cpu(), Y64) < 1e-5
+    assert rel_l2(hd.grad.cpu(), h64.grad) < 2e-4
