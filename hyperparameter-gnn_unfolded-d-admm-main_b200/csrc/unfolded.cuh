@@ -56,22 +56,28 @@ __device__ __forceinline__ float pow2_of(int e) { return __uint_as_float((unsign
 
 template <int VEC>
 __device__ __forceinline__ void store_split(const SplitOut& sp, unsigned off, const Vec<float, VEC>& v, float s1, float s2) {
-    __half h[VEC], l[VEC];
+    const float sc = s1 * s2;                      // 2^e with |e| <= 115: a normal float, the product is exact
+    if constexpr (VEC % 2 == 0) {
+        __half2 h[VEC / 2], l[VEC / 2];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const float x = v.v[j] * s1 * s2;
-        h[j] = __float2half_rn(x);
-        l[j] = __float2half_rn(x - __half2float(h[j]));
-    }
-    if constexpr (VEC == 4) {
-        *reinterpret_cast<uint2*>(sp.hi + off) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(sp.lo + off) = *reinterpret_cast<const uint2*>(l);
-    } else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            sp.hi[off + j] = h[j];
-            sp.lo[off + j] = l[j];
+        for (int j = 0; j < VEC / 2; ++j) {
+            const float x0 = v.v[2 * j] * sc, x1 = v.v[2 * j + 1] * sc;
+            h[j] = __floats2half2_rn(x0, x1);                       // one packed conversion per pair
+            const float2 hf = __half22float2(h[j]);
+            l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
         }
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<uint2*>(sp.hi + off) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(sp.lo + off) = *reinterpret_cast<const uint2*>(l);
+        } else {
+            *reinterpret_cast<__half2*>(sp.hi + off) = h[0];
+            *reinterpret_cast<__half2*>(sp.lo + off) = l[0];
+        }
+    } else {
+        const float x = v.v[0] * sc;
+        const __half h = __float2half_rn(x);
+        sp.hi[off] = h;
+        sp.lo[off] = __float2half_rn(x - __half2float(h));
     }
 }
 
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     }
 
     struct Row { V a, atb, U, y, d; };
-    unsigned bad = 0;
+    T nonfinite = (T)0;
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         if (b >= p.B) break;
@@ -319,12 +325,14 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
                 rr = add_rn(rr, mul_rn(sign_of(y), tau));
                 rr = add_rn(rr, mul_rn(U, dg));
                 rr = add_rn(rr, mul_rn(dv.v[v], rho));
-                const T g = clamp_sym(rr, p.G);
-                const T z = clamp_sym(sub_rn(y, mul_rn(alpha, g)), p.V);
+                // min/max clamps: identical to torch.clamp for finite values; a NaN would be swallowed, so the raw
+                // gradient joins the non-finite accumulator below (0*x is NaN iff x is Inf/NaN) and any hit sends the
+                // batch to the guarded per-iteration path (reference guards :55-61,84-86,102-104)
+                const T g = fmin(fmax(rr, -p.G), p.G);
+                const T z = fmin(fmax(sub_rn(y, mul_rn(alpha, g)), -p.V), p.V);
                 rv.v[v] = rr;
                 yn.v[v] = z;
-                // non-finite detection (reference guards): y or U not finite, gradient NaN, y+ not finite
-                bad |= (finite_val(y) ? 0u : 1u) | (finite_val(U) ? 0u : 2u) | ((g != g) ? 4u : 0u) | (finite_val(z) ? 0u : 8u);
+                nonfinite = fma(y, (T)0, fma(U, (T)0, fma(rr, (T)0, nonfinite)));
             }
             if (act_i) {
                 st_vec<T, VEC>(p.y_next + off, yn);
@@ -345,7 +353,9 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
         if (p.sp.amax_out) publish_amax(amax_bits, p.sp.amax_out, sAmax);
     }
     if (p.flags) {
-        bad = __reduce_or_sync(0xffffffffu, bad);
+        // the fused path only reports "something was not finite" (all bits): the modules then re-run the batch on
+        // the guarded per-iteration path, whose step kernel reports the individual conditions
+        const unsigned bad = __reduce_or_sync(0xffffffffu, (nonfinite != (T)0) ? 0xFu : 0u);
         if (bad && lane == 0) atomicOr(p.flags, (int)bad);
     }
 }
