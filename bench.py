@@ -285,7 +285,7 @@ def run_ours(opt, w):
     value = w["K"] * B_glob / t_dev
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
             "ms_per_step": 1e3 * t_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if opt.algo != "fast" else "f16-operands/f32-accumulate (flagged reduced precision)", "data": "synthetic",
             "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": B_glob,
                        "batch_per_gpu": B_loc, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "contraction": opt.algo, "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
@@ -363,7 +363,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc", "f16", "fast"],
+                    help="contraction kernel; 'fast' is the FLAGGED reduced-precision mode (fp16 operands, 1e-2 class) and is "
+                         "never the default: the headline number is measured in fp32-parity mode")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     opt = ap.parse_args()
     w = WORKLOADS[opt.workload]

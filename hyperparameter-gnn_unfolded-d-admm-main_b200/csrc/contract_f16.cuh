@@ -132,6 +132,7 @@ struct Params {
     const int *exp_w, *exp_x;      // device: scale exponents of the two operands
     unsigned* amax_out;            // device, optional: running max |out| bits (feeds the next operand split's bound)
     const float* sub;              // device, optional [B,P,n_out] laid out like `out`: out = W x - sub (the Atb term)
+    int fast;                      // 1: flagged reduced-precision mode -- hi*hi only (fp16 operands, 2^-11), one MMA per k-step
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -201,11 +202,13 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
 #elif defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT == 3
                     if (rank == 0) mbar_arrive(full_bar(stage));                // timing experiment: no TMA at all
 #else
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), p.fast ? STAGE : 2 * STAGE);
                     tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
                     tma_load_3d_pair(sb + TILE, &map_xh, lead, kb * BKE, ag, b0);
-                    tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
-                    tma_load_3d_pair(sb + 3 * TILE, &map_xl, lead, kb * BKE, ag, b0);
+                    if (!p.fast) {
+                        tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
+                        tma_load_3d_pair(sb + 3 * TILE, &map_xl, lead, kb * BKE, ag, b0);
+                    }
 #endif
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -231,9 +234,14 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                             const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the 64-byte swizzled row
                             const uint64_t da = tile_desc(sa + koff), db = tile_desc(sb + koff);
                             const uint64_t da_lo = tile_desc(sa_lo + koff), db_lo = tile_desc(sb_lo + koff);
-                            umma_f16_pair(d_tmem, da_lo, db, (kb != ch * KB_PER_CHUNK) || ks != 0);
-                            umma_f16_pair(d_tmem, da, db_lo, 1u);
-                            umma_f16_pair(d_tmem, da, db, 1u);
+                            const uint32_t acc_in = (kb != ch * KB_PER_CHUNK) || ks != 0;
+                            if (!p.fast) {
+                                umma_f16_pair(d_tmem, da_lo, db, acc_in);
+                                umma_f16_pair(d_tmem, da, db_lo, 1u);
+                                umma_f16_pair(d_tmem, da, db, 1u);
+                            } else {
+                                umma_f16_pair(d_tmem, da, db, acc_in);
+                            }
                         }
                         umma_commit_pair(empty_bar(stage));
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -383,7 +391,7 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 // out[b,p,:] (+)= W_p x[b,p,:] from prepared operands: wprep = split of W viewed as [P*n_out][n_in],
 // xprep = split of x viewed as [B*P][n_in]
 inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
-                  cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr) {
+                  cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr, int fast = 0) {
     tc::EncodeTiledFn enc = tc::encode_fn();
     if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
     const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
@@ -400,7 +408,7 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     p.n_tiles = ceil_div(B, 256);
     p.k_blocks = ceil_div(n_in, BKE);
     p.total_tiles = P * p.m_tiles * p.n_tiles;
-    p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub;
+    p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub; p.fast = fast;
     static int num_sms = [] {
         int dev = 0, n = 148;
         cudaGetDevice(&dev);

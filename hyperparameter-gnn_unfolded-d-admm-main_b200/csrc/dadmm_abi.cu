@@ -213,7 +213,7 @@ static int resolve_algo(int dtype, int algo, int B, int P, int n_out, int n_in, 
     if (dtype != DADMM_F32 || algo == DADMM_ALGO_SIMT) return DADMM_ALGO_SIMT;
     const bool f16_ok = tc_layout && f16::dims_supported(B, P, n_out, n_in);
     const bool tf32_ok = tc_layout && tc::dims_supported(B, P, n_out, n_in);
-    if (algo == DADMM_ALGO_TC_3XF16) return f16_ok ? DADMM_ALGO_TC_3XF16 : -1;
+    if (algo == DADMM_ALGO_TC_3XF16 || algo == DADMM_ALGO_TC_F16X1) return f16_ok ? algo : -1;
     if (algo == DADMM_ALGO_TC_3XTF32) return tf32_ok ? DADMM_ALGO_TC_3XTF32 : -1;
     static const int prefer = [] {                       // DADMM_TC_PREFER=tf32 keeps AUTO on the 3xTF32 kernels
         const char* e = getenv("DADMM_TC_PREFER");
@@ -225,7 +225,8 @@ static int resolve_algo(int dtype, int algo, int B, int P, int n_out, int n_in, 
 }
 
 static size_t contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in) {
-    if (resolve_algo(dtype, algo, B, P, n_out, n_in, true) != DADMM_ALGO_TC_3XF16) return 0;
+    const int ra = resolve_algo(dtype, algo, B, P, n_out, n_in, true);
+    if (ra != DADMM_ALGO_TC_3XF16 && ra != DADMM_ALGO_TC_F16X1) return 0;
     return f16::split_bytes((long long)P * n_out, n_in) + f16::split_bytes((long long)B * P, n_in);
 }
 
@@ -238,7 +239,7 @@ static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in,
     if (!W || !x || !out) DADMM_FAIL(-1, "contract: null pointer");
     if (dtype != DADMM_F32 && dtype != DADMM_F64) DADMM_FAIL(-1, "contract: unknown dtype %d", dtype);
     if (dtype == DADMM_F64) {
-        if (algo == DADMM_ALGO_TC_3XTF32 || algo == DADMM_ALGO_TC_3XF16) DADMM_FAIL(-4, "contract: tensor-core paths are fp32 only");
+        if (algo >= DADMM_ALGO_TC_3XTF32) DADMM_FAIL(-4, "contract: tensor-core paths are fp32 only");
         GemmParams<double> p{B, P, n_out, n_in, (const double*)W, w_sp, w_si, w_sk, (const double*)x, x_sb, x_sp, x_sk,
                              (double*)out, o_sb, o_sp, o_si, accumulate};
         return launch_contract_simt<double>(p, s);
@@ -247,14 +248,14 @@ static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in,
                                                x_sb, x_sp, x_sk, out, o_sb, o_sp, o_si);
     const int ra = resolve_algo(dtype, algo, B, P, n_out, n_in, tc_layout && x_sb == (int64_t)P * n_in);
     if (ra < 0) DADMM_FAIL(-4, "contract: shape/layout not supported by the requested tensor-core kernel");
-    if (ra == DADMM_ALGO_TC_3XF16) {
+    if (ra == DADMM_ALGO_TC_3XF16 || ra == DADMM_ALGO_TC_F16X1) {
         const size_t wb = f16::split_bytes((long long)P * n_out, n_in), xb = f16::split_bytes((long long)B * P, n_in);
         if (!ws || ws_bytes < wb + xb) DADMM_FAIL(-1, "contract: workspace too small for the fp16 operand copies");
         char* c = (char*)ws;
         if (!w_prepared)
             if (int e = f16::split_tensor((const float*)W, (long long)P * n_out, n_in, n_in, c, s)) return e;
         if (int e = f16::split_tensor((const float*)x, (long long)B * P, n_in, n_in, c + wb, s)) return e;
-        return f16::launch(B, P, n_out, n_in, c, c + wb, (float*)out, o_sb, accumulate, s);
+        return f16::launch(B, P, n_out, n_in, c, c + wb, (float*)out, o_sb, accumulate, s, nullptr, nullptr, ra == DADMM_ALGO_TC_F16X1);
     }
     if (ra == DADMM_ALGO_TC_3XTF32)
         return tc::launch(B, P, n_out, n_in, (const float*)W, (const float*)x, (float*)out, x_sb, o_sb, accumulate, ws, ws_bytes, s);
@@ -379,7 +380,9 @@ static size_t amax_slots_bytes(int K) { return ((size_t)(K + 1) * 4 + 255) / 256
 
 // the fused fp16 path: operands of the contraction are produced already split by the level kernels
 static bool fused_f16(int dtype, int algo, int B, int P, int n) {
-    return dtype == DADMM_F32 && (n % 8) == 0 && resolve_algo(dtype, algo, B, P, n, n, true) == DADMM_ALGO_TC_3XF16;
+    if (dtype != DADMM_F32 || (n % 8) != 0) return false;
+    const int ra = resolve_algo(dtype, algo, B, P, n, n, true);
+    return ra == DADMM_ALGO_TC_3XF16 || ra == DADMM_ALGO_TC_F16X1;
 }
 
 template <typename T>
@@ -418,7 +421,8 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         // stream (R_save[k]) -- the forward level neither reads Atb nor writes r_k; the backward rebuilds r_k from a_k'
         char* ak = (fused && R_save) ? (char*)R_save + (size_t)k * NB : a;
         if (fused) {
-            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)ak, sPn, 0, s, nullptr, (const float*)Atb)) return e;
+            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)ak, sPn, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1))
+                return e;
             if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
         } else {
             if (int e = contract_impl(dtype, algo, B, P, n, n, W, (int64_t)n * n, sn, 1, yk, sPn, sn, 1, a, sPn, sn, 1, 0, w8, cw, s, k > 0))
@@ -491,7 +495,8 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         }
         if (k > 0) {
             if (fused) {
-                if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)Tb, sPn, 1, s, slots + (k - 1))) return e;
+                if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)Tb, sPn, 1, s, slots + (k - 1), nullptr, algo == DADMM_ALGO_TC_F16X1))
+                    return e;
             } else {
                 if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s,
                                           k < K - 1))
@@ -562,7 +567,7 @@ size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int
 
 int dadmm_contract_uses_tensor_cores(int dtype, int algo, int B, int P, int n_out, int n_in) {
     const int ra = resolve_algo(dtype, algo, B, P, n_out, n_in, true);
-    return (ra == DADMM_ALGO_TC_3XTF32 || ra == DADMM_ALGO_TC_3XF16) ? ra : 0;
+    return (ra >= DADMM_ALGO_TC_3XTF32) ? ra : 0;
 }
 
 int dadmm_step_fwd(int dtype, int B, int P, int n, const dadmm_graph* graph, const dadmm_clamps* clamps,

@@ -16,9 +16,10 @@ LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so
 
 ABI_VERSION = 2
 F32, F64 = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16 = 0, 1, 2, 3
+ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
-         "f16": ALGO_TC_3XF16, "tc_3xf16": ALGO_TC_3XF16}
+         "f16": ALGO_TC_3XF16, "tc_3xf16": ALGO_TC_3XF16,
+         "fast": ALGO_TC_F16X1, "f16x1": ALGO_TC_F16X1}      # "fast": flagged reduced-precision mode (1e-2 class)
 FLAG_Y, FLAG_U, FLAG_GRAD, FLAG_YNEXT = 1, 2, 4, 8
 
 

@@ -46,7 +46,9 @@ enum {
     DADMM_ALGO_AUTO = 0,      /* tcgen05 when the shape allows it (fp32 only), else SIMT          */
     DADMM_ALGO_SIMT = 1,      /* FP32/FP64 FMA pipe, exact IEEE accumulation in k order           */
     DADMM_ALGO_TC_3XTF32 = 2, /* tcgen05.mma kind::tf32, hi/lo split of both operands (3 MMAs)    */
-    DADMM_ALGO_TC_3XF16 = 3   /* tcgen05.mma kind::f16 on scaled fp16 hi/lo pairs (3 MMAs, 2x tf32 rate) */
+    DADMM_ALGO_TC_3XF16 = 3,  /* tcgen05.mma kind::f16 on scaled fp16 hi/lo pairs (3 MMAs, 2x tf32 rate) */
+    DADMM_ALGO_TC_F16X1 = 4   /* FLAGGED reduced precision (1e-2 class): fp16 operands, one MMA, fp32 accumulate;
+                                 never chosen by AUTO */
 };
 
 /* non-finite bits OR-ed into `flags` by the step kernel (reference guards,

@@ -443,3 +443,34 @@ def test_edge_shapes_match_oracle(B, P, n, K, kind):
     (Y * gYr.to(DEV)).sum().backward()
     assert rel_l2(Y.cpu(), Y64) < 1e-5
     assert rel_l2(hd.grad.cpu(), h64.grad) < 2e-4
+
+
+def test_flagged_reduced_precision_mode():
+    """algo="fast" (fp16 operands, one MMA, fp32 accumulate): the north star's flagged reduced-precision mode,
+    1e-2 relative; never selected by "auto"."""
+    DF, BG = _df()
+    from dadmm_b200 import _lib
+    assert _lib.lib.dadmm_contract_uses_tensor_cores(0, _lib.ALGO_AUTO, 256, 4, 256, 256) != _lib.ALGO_TC_F16X1
+    P, n, m, K, B = 4, 256, 64, 8, 256
+    pr = random_problem(P, n, m, B, K, seed=33, a_scale=0.1)
+    hyp = O.hyp_table(pr["param"], torch.tensor([0.1, 0.99, 0.99, 0.99]), True)
+    A = pr["A"].to(DEV)
+    W = DF.atx(A, A)[0].contiguous()
+    x = _dev(pr["y0"]) * 100
+    ref = DF.contract(W, x, algo="simt")
+    fast = DF.contract(W, x, algo="fast")
+    e = rel_l2(fast.cpu(), ref.cpu())
+    assert 1e-6 < e < 2e-3, e                       # fp16-grade, and really the one-term kernel
+    graph = BG.from_graph_list(pr["graphs"], P, DEV)
+    clamps = [DF.clamps_model1(k) for k in range(K)]
+    outs = {}
+    for algo in ("simt", "fast"):
+        h = hyp.to(DEV).requires_grad_(True)
+        Y = DF.Unfolded.apply(h, W, W.transpose(1, 2).contiguous(), DF.atx(A, pr["b"].to(DEV)).squeeze(-1), _dev(pr["y0"]),
+                              _dev(pr["U0"]), _dev(pr["d0"]), graph, clamps, algo, None, None)
+        losses = DF.MSELoss.apply(Y, pr["label"].to(DEV), None, None)
+        losses[-1].backward()
+        outs[algo] = (Y.detach().cpu(), h.grad.cpu(), float(losses[-1]))
+    assert rel_l2(outs["fast"][0], outs["simt"][0]) < 1e-2
+    assert rel_l2(outs["fast"][1], outs["simt"][1]) < 1e-2
+    assert abs(outs["fast"][2] - outs["simt"][2]) < 1e-2 * abs(outs["simt"][2])
