@@ -112,6 +112,7 @@ __device__ __forceinline__ void publish_amax(unsigned m, unsigned* out, unsigned
 template <typename T>
 struct LevelFwdParams {
     int B, P, n, TB, first, list_cap;   // list_cap: shared-memory ints reserved per problem for its neighbour list
+    int csplit;                         // CTAs per problem group (each walks nchunks/csplit consecutive chunks)
     const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // event lists (exact order)
     const T *hyp_k, *hyp_prev;          // rows [P,4] of the table
     T G, V, D, Uc_prev;
@@ -125,6 +126,7 @@ struct LevelFwdParams {
 template <typename T>
 struct LevelBwdParams {
     int B, P, n, TB, first, top, list_cap;
+    int csplit;                         // CTAs per problem group: each CTA walks nchunks/csplit consecutive 128-unknown chunks
     const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // plain adjacency lists
     const T *hyp_k, *hyp_prev;
     T G, V, D, Uc_prev;
@@ -216,6 +218,19 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
 #define DADMM_LEVEL_MINB_BWD 3      // no prefetch: 3 -> 1.78 ms (80 regs, no spills), 4 -> 2.10 (spills)
 #endif
 
+// first two levels of warp_sum4: afterwards lane l holds the sum over lanes {l, l^8, l^16, l^24} of value (l >> 3)
+template <typename T>
+__device__ __forceinline__ T warp_sum4_partial(T a, T b, T c, T d, int lane) {
+    const bool hi = lane & 16;
+    T k0 = hi ? c : a, k1 = hi ? d : b;
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? a : c, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? b : d, 16);
+    const bool h8 = lane & 8;
+    T k = h8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+    return k;
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_kernel(const LevelFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -228,10 +243,10 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int lane_bytes = lane * VEC * (int)sizeof(T);
     const int nchunks = (p.n + CH - 1) / CH;
-    const int chunk = blockIdx.x % nchunks;
-    const int b0 = (blockIdx.x / nchunks) * p.TB;
-    const int i = chunk * CH + lane * VEC;
-    const bool act_i = i < p.n;
+    const int cs = blockIdx.x % p.csplit;               // a CTA walks a contiguous range of chunks of its problems
+    const int b0 = (blockIdx.x / p.csplit) * p.TB;
+    const int cpc = (nchunks + p.csplit - 1) / p.csplit;
+    const int chunk_begin = cs * cpc, chunk_end = min(nchunks, chunk_begin + cpc);
     const bool first = p.first != 0;
     __shared__ unsigned sAmax[32];
     __shared__ float sAlpha[32];
@@ -256,8 +271,14 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     unsigned amax_bits = 0;
 
     const bool staged = p.list_cap > 0;
+    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    T nonfinite = (T)0;
+
+    for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+    const int i = chunk * CH + lane * VEC;
+    const bool act_i = i < p.n;
     if (!first) {
-        if (staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+        if (chunk != chunk_begin) __syncthreads();      // rows of the previous chunk are still being read
         for (int bl = 0; bl < p.TB; ++bl) {
             const int b = b0 + bl;
             const T* src = p.y + (((unsigned)b * P) * p.n + i);
@@ -271,7 +292,6 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     }
 
     struct Row { V a, atb, U, y, d; };
-    T nonfinite = (T)0;
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         if (b >= p.B) break;
@@ -349,6 +369,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
 #endif
         }
     }
+    }   // chunk loop
     if constexpr (sizeof(T) == 4) {
         if (p.sp.amax_out) publish_amax(amax_bits, p.sp.amax_out, sAmax);
     }
@@ -368,15 +389,19 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     const int P = p.P, R = p.TB * P;
     unsigned char* S0 = smem_raw;                                   // y_k tile
     unsigned char* S1 = S0 + (size_t)R * CH * sizeof(T);            // adjoint of the unclamped 2L y_k
-    int32_t* sPtr = reinterpret_cast<int32_t*>(S1 + (size_t)R * CH * sizeof(T));
+    T* sAcc = reinterpret_cast<T*>(S1 + (size_t)R * CH * sizeof(T));   // [R][32]: per-row, per-lane partial sums of d/d hyp
+    int32_t* sPtr = reinterpret_cast<int32_t*>(sAcc + (size_t)R * 32);
     int32_t* sIdx = sPtr + p.TB * (P + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int lane_bytes = lane * VEC * (int)sizeof(T);
     const int nchunks = (p.n + CH - 1) / CH;
-    const int chunk = blockIdx.x % nchunks;
-    const int b0 = (blockIdx.x / nchunks) * p.TB;
-    const int i = chunk * CH + lane * VEC;
-    const bool act_i = i < p.n;
+    // A CTA owns TB problems and walks a contiguous range of chunks: the neighbour lists, the split scale and
+    // max|alpha| are set up once, and the four hyper-parameter sums of a row are accumulated per lane in shared
+    // memory across the chunks (one shuffle tree + one partial-sum row per CTA instead of one per chunk).
+    const int cs = blockIdx.x % p.csplit;
+    const int b0 = (blockIdx.x / p.csplit) * p.TB;
+    const int cpc = (nchunks + p.csplit - 1) / p.csplit;
+    const int chunk_begin = cs * cpc, chunk_end = min(nchunks, chunk_begin + cpc);
     const bool first = p.first != 0, top = p.top != 0;
     __shared__ float sAlpha[32];
 
@@ -396,6 +421,12 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
 
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    for (int r = threadIdx.x; r < R * 32; r += blockDim.x) sAcc[r] = (T)0;
+
+    for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+    const int i = chunk * CH + lane * VEC;
+    const bool act_i = i < p.n;
+    if (chunk != chunk_begin) __syncthreads();          // the previous chunk's last phase still reads the tiles
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         const T* src = p.y + (((unsigned)b * P) * p.n + i);
@@ -507,14 +538,13 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
                     st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
                 }
             }
-            const T s = warp_sum4(pa, pt, pr, pe, lane);
-            if ((lane & 7) == 0) p.partials[(((unsigned)chunk * p.B + b) * P + pp) * 4 + (lane >> 3)] = s;
+            sAcc[(bl * P + pp) * 32 + lane] += warp_sum4_partial(pa, pt, pr, pe, lane);
 #if DADMM_LEVEL_BWD_PREFETCH
             cur = nxt;
 #endif
         }
     }
-    if (first) return;
+    if (!first) {
     __syncthreads();
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
@@ -533,6 +563,21 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
                 for (int v = 0; v < VEC; ++v) s.v[v] += lt.v[v];
                 st_vec<T, VEC>(p.Tb + off, s);
             }
+        }
+    }
+    }   // !first
+    }   // chunk loop
+
+    // finish the per-row sums: 8 lanes per sum -> lanes 0/8/16/24 hold (d alpha, d tau, d rho, d eta_prev)
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        if (b >= p.B) break;
+        for (int pp = warp; pp < P; pp += nwarps) {
+            T k = sAcc[(bl * P + pp) * 32 + lane];
+            k += __shfl_xor_sync(0xffffffffu, k, 4);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            if ((lane & 7) == 0) p.partials[(((unsigned)cs * p.B + b) * P + pp) * 4 + (lane >> 3)] = k;
         }
     }
 }
