@@ -203,6 +203,8 @@ def run_ours(opt, w):
     b_host, label_host = b_dev.cpu().pin_memory(), label_h.pin_memory()
     model = unfolded_DLASSO.DLASSO_unfolded(A_dev, args).to(dev)
     model.contract_algo = opt.algo
+    model.two_stage = not opt.one_stage
+    two_stage = bool(model.two_stage and _lib.lib.dadmm_unfolded_uses_factor(0, _lib.ALGOS[opt.algo], B_loc, w["P"], w["n"], w["m"]))
     with torch.no_grad():
         model.seq_hyp.param.copy_(param)
     optim = torch.optim.Adam(model.parameters(), lr=1e-4)
@@ -276,7 +278,7 @@ def run_ours(opt, w):
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     t_prof = p0.elapsed_time(p1)
-    roofline, breakdown = make_roofline(w, B_loc, prof, t_prof)
+    roofline, breakdown = make_roofline(w, B_loc, prof, t_prof, two_stage)
 
     if rank != 0:
         if world > 1:
@@ -288,7 +290,7 @@ def run_ours(opt, w):
             "dtype": "f32" if opt.algo != "fast" else "f16-operands/f32-accumulate (flagged reduced precision)", "data": "synthetic",
             "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": B_glob,
                        "batch_per_gpu": B_loc, "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "contraction": opt.algo, "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
+                       "contraction": opt.algo + (" two-stage A^T(A y)" if two_stage else " AtA y"), "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
                        if B_loc * w["P"] * w["n"] * 4 > 126e6 else "working set fits L2 (small config)",
                        "step": "forward K iters + compute_loss + loss_final.backward + grad allreduce + Adam"},
             "clocks": clocks,
@@ -308,9 +310,10 @@ def run_ours(opt, w):
         dist.destroy_process_group()
 
 
-def make_roofline(w, B_loc, prof, t_step_ms):
+def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False):
     """Roofline of the dominant kernel of the step, from the profiled extra step.
-    Contraction (tensor / FMA bound): algorithmic flops per launch = 2*P*n*n*B_loc.
+    Contraction (tensor / FMA bound): algorithmic flops per launch = 2*P*n*n*B_loc (AtA y), or 2*P*m*n*B_loc for each
+    of the two launches of the two-stage form A^T (A y)  (F = P*min(2n^2, 4mn) per contraction).
     Step kernels (HBM bound): algorithmic bytes per iteration*problem = 20*P*n fwd, 36*P*n bwd."""
     peaks = {}
     try:
@@ -323,14 +326,17 @@ def make_roofline(w, B_loc, prof, t_step_ms):
     P, n = w["P"], w["n"]
     breakdown = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof.items() if v[1]}
     breakdown["step_total_ms"] = round(t_step_ms, 3)
+    prof = dict(prof)
+    if prof.get("contract_stage1", (0, 0))[1]:          # two-stage contraction: both launches belong to the contraction
+        prof["contract_tc"] = (prof["contract_tc"][0] + prof["contract_stage1"][0], prof["contract_tc"][1] + prof["contract_stage1"][1])
     kind = max(("contract_simt", "contract_tc", "step_fwd", "step_bwd"), key=lambda k: prof[k][0])
     ms, cnt = prof[kind]
     if kind.startswith("contract"):
-        flops = 2.0 * P * n * n * B_loc
+        flops = 2.0 * P * (w["m"] if two_stage else n) * n * B_loc
         ach = flops / (ms / cnt * 1e-3) / 1e12
-        note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). A 3xTF32 "
-                "tcgen05 kernel issues 3 tf32 MMAs at half the bf16 rate, so 1/6 of this peak is its ceiling; "
-                "the SIMT kernel's ceiling is the FP32 FMA pipe (~60-70 TFLOP/s)")
+        note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). The default kernel "
+                "issues 3 fp16 MMAs per product (scaled hi/lo operand pairs), so 1/3 of this peak is its ceiling "
+                "(3xTF32: 1/6; the SIMT kernel's ceiling is the FP32 FMA pipe, ~60-70 TFLOP/s)")
         roof = {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
                 "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
                 "share_of_step": ms / t_step_ms, "note": note}
@@ -367,6 +373,8 @@ def main():
                     help="contraction kernel; 'fast' is the FLAGGED reduced-precision mode (fp16 operands, 1e-2 class) and is "
                          "never the default: the headline number is measured in fp32-parity mode")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--one-stage", action="store_true",
+                    help="keep the contraction on the explicit AtA operator (A/B switch for the two-stage form A^T (A y))")
     opt = ap.parse_args()
     w = WORKLOADS[opt.workload]
     if opt.impl == "reference":

@@ -36,7 +36,7 @@ extern std::atomic<long long> g_launches;
 // Optional per-kernel-kind timing (dadmm_profile_enable / dadmm_profile_read): when enabled, every
 // launch is bracketed by a pair of CUDA events recorded on the launching stream.
 enum ProfKind { PROF_CONTRACT_SIMT = 0, PROF_CONTRACT_TC = 1, PROF_STEP_FWD = 2, PROF_STEP_BWD = 3,
-                PROF_REDUCE_HYP = 4, PROF_LOSS = 5, PROF_SPLIT = 6, PROF_KINDS = 8 };
+                PROF_REDUCE_HYP = 4, PROF_LOSS = 5, PROF_SPLIT = 6, PROF_CONTRACT_STAGE1 = 7, PROF_KINDS = 8 };
 void prof_begin(int kind, cudaStream_t s);
 void prof_end(cudaStream_t s);
 struct ProfScope {

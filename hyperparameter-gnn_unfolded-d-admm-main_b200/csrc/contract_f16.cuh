@@ -38,9 +38,16 @@ constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 constexpr int THREADS = 384;                     // warps 0-3: TMA, MMA, (2 idle); warps 4-11: accumulate + store
 constexpr int EPI_WARP0 = 4;
 #ifndef DADMM_F16_KB_PER_CHUNK
-#define DADMM_F16_KB_PER_CHUNK (DADMM_F16_BK64 ? 1 : 2)
+#define DADMM_F16_KB_PER_CHUNK (DADMM_F16_BK64 ? 2 : 4)
 #endif
-constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;   // 2 x 32 = 64 k per tensor-core partial sum
+// k-blocks per tensor-core partial sum (Params::kbc; kb_per_chunk(): 2 x 64 = 128 k for long contractions, 64 k for
+// short ones).  The TMEM accumulator truncates on
+// every accumulation, so what matters is how many FULL-MAGNITUDE accumulations a partial sum sees: inside a k-block
+// the two correction products (lo*hi, hi*lo: 2^-11 of the main term) of all k-steps are issued before the hi*hi
+// products, i.e. into a still-small accumulator where their truncation is negligible.  B200, cfg4 shapes:
+// 64-k chunks 0.98 ms per two-stage contraction, 128-k 0.86 ms, 256-k 0.82 ms (the 128 KB TMEM drain per chunk,
+// not the MMA, paces the short chunks).
+constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;
 constexpr int COLS_PER_THREAD = 128;
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
@@ -71,29 +78,40 @@ __device__ __forceinline__ int scale_exponent(unsigned amax_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }
 
-// x [rows][n] fp32 (row stride ld) -> hi, lo [rows][n_pad] fp16 with the tensor's scale; writes the exponent
+// x [rows][n] fp32 (row stride ld) -> hi, lo [rows][n_pad] fp16 with the tensor's scale; writes the exponent and,
+// when l1_out is given, max_r sum_i |x[r][i]| as float bits (the operator bound of a two-stage contraction)
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, long long rows, int n, long long ld,
                                                         int n_pad, const unsigned* __restrict__ amax_bits,
-                                                        __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ exp_out) {
+                                                        __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ exp_out,
+                                                        unsigned* __restrict__ l1_out) {
     const int e = scale_exponent(*amax_bits);
     // 2^e can exceed the float range for tiny tensors; apply it in two factors
     const float s1 = pow2f(e / 2), s2 = pow2f(e - e / 2);
     if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float l1max = 0.f;
     for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
         const float* xr = x + r * ld;
         __half* hr = hi + r * n_pad;
         __half* lr = lo + r * n_pad;
+        float l1 = 0.f;
         for (int i = lane * 2; i < n_pad; i += 64) {
             float v0 = (i < n) ? xr[i] : 0.f, v1 = (i + 1 < n) ? xr[i + 1] : 0.f;
+            l1 += fabsf(v0) + fabsf(v1);
             v0 = v0 * s1 * s2;
             v1 = v1 * s1 * s2;
             const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1h = __float2half_rn(v1 - __half2float(h1));
             *reinterpret_cast<__half2*>(hr + i) = __halves2half2(h0, h1);
-            *reinterpret_cast<__half2*>(lr + i) = __halves2half2(l0, l1);
+            *reinterpret_cast<__half2*>(lr + i) = __halves2half2(l0, l1h);
+        }
+        if (l1_out) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            l1max = fmaxf(l1max, l1);
         }
     }
+    if (l1_out && lane == 0 && l1max > 0.f) atomicMax(l1_out, __float_as_uint(l1max));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -133,6 +151,14 @@ struct Params {
     unsigned* amax_out;            // device, optional: running max |out| bits (feeds the next operand split's bound)
     const float* sub;              // device, optional [B,P,n_out] laid out like `out`: out = W x - sub (the Atb term)
     int fast;                      // 1: flagged reduced-precision mode -- hi*hi only (fp16 operands, 2^-11), one MMA per k-step
+    int kbc;                       // k-blocks per tensor-core partial sum
+    // first stage of a two-stage contraction  out = F2 (F1 x):  t = F1 x leaves the kernel as the fp16 split the
+    // second stage consumes ([B*P][t_ld] hi and lo), scaled with an exponent every thread derives from the rigorous
+    // bound |t| <= max|x| * max_row ||F1 row||_1  (t_hi == nullptr: plain fp32 output)
+    __half *t_hi, *t_lo;
+    int t_ld;
+    int* t_exp;                    // device: exponent of the t split (written by one thread)
+    const unsigned* w_l1;          // device: max row L1 norm of the operator, float bits
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -176,7 +202,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int tiles_per_agent = p.m_tiles * p.n_tiles;
-    const int n_chunks = (p.k_blocks + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+    const int n_chunks = (p.k_blocks + p.kbc - 1) / p.kbc;
 
     if (warp < EPI_WARP0) {
         reg_dec<40>();
@@ -224,23 +250,30 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                     mbar_wait(tempty_bar(buf), ((uint32_t)(ci >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256;
-                    const int kb_end = min(p.k_blocks, (ch + 1) * KB_PER_CHUNK);
-                    for (int kb = ch * KB_PER_CHUNK; kb < kb_end; ++kb) {
+                    const int kb_end = min(p.k_blocks, (ch + 1) * p.kbc);
+                    for (int kb = ch * p.kbc; kb < kb_end; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tcgen05_fence_after();
                         const uint32_t sa = stage_base(stage), sb = sa + TILE, sa_lo = sa + 2 * TILE, sb_lo = sa + 3 * TILE;
+                        const bool fresh = kb == ch * p.kbc;           // first k-block of the partial sum: accumulator starts at 0
+                        if (!p.fast) {
+                            // corrections first (see KB_PER_CHUNK): 2 x BKE/16 small accumulations, then BKE/16 full-size ones
 #pragma unroll
-                        for (int ks = 0; ks < BKE / 16; ++ks) {
-                            const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the 64-byte swizzled row
-                            const uint64_t da = tile_desc(sa + koff), db = tile_desc(sb + koff);
-                            const uint64_t da_lo = tile_desc(sa_lo + koff), db_lo = tile_desc(sb_lo + koff);
-                            const uint32_t acc_in = (kb != ch * KB_PER_CHUNK) || ks != 0;
-                            if (!p.fast) {
-                                umma_f16_pair(d_tmem, da_lo, db, acc_in);
-                                umma_f16_pair(d_tmem, da, db_lo, 1u);
-                                umma_f16_pair(d_tmem, da, db, 1u);
-                            } else {
-                                umma_f16_pair(d_tmem, da, db, acc_in);
+                            for (int ks = 0; ks < BKE / 16; ++ks) {
+                                const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the swizzled row
+                                umma_f16_pair(d_tmem, tile_desc(sa_lo + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u);
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb_lo + koff), 1u);
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < BKE / 16; ++ks) {
+                                const uint32_t koff = ks * 32;
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < BKE / 16; ++ks) {
+                                const uint32_t koff = ks * 32;
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u);
                             }
                         }
                         umma_commit_pair(empty_bar(stage));
@@ -258,6 +291,18 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
         const int es = -(__ldg(p.exp_w) + __ldg(p.exp_x));           // undo both operand scales (exact: powers of two)
         const float unscale = pow2f(es / 2), unscale2 = pow2f(es - es / 2);
         const float rescale = pow2f(-es / 2), rescale2 = pow2f(-es + es / 2);
+        float tscale = 1.f, tscale2 = 1.f;
+        if (p.t_hi) {
+            // |x| 2^exp_x < 2^14 by construction of every split, so |t| < 2^(14 - exp_x) * L1(F1); 1 % covers the fp32
+            // rounding of the L1 sum
+            const int ex = max(-112, min(126, 14 - __ldg(p.exp_x)));
+            const float bound = pow2f(ex) * (__uint_as_float(__ldg(p.w_l1)) * 1.01f);
+            const int et = scale_exponent(__float_as_uint(bound));
+            const int ts = et + es;                                   // accumulators hold t * 2^(exp_w + exp_x)
+            tscale = pow2f(ts / 2);
+            tscale2 = pow2f(ts - ts / 2);
+            if (blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) *p.t_exp = et;
+        }
         int ci = 0;
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
@@ -266,6 +311,10 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             const int i = i0 + q * 32 + lane;
             float* orow = p.out + (long long)ag * p.n_out + i;
             const bool seeded = p.accumulate || p.sub != nullptr;
+            // full tile: every (i, b) of this thread is in range -- no per-element predicates, addresses by pointer stepping
+            // (ncu, round 1: the guarded 64-bit index form cost ~16 instructions per load and ~20 per store and made the
+            // short-K second stage of a two-stage contraction issue-bound in its epilogue)
+            const bool full = (i0 + 128 <= p.n_out) && (b0 + COLS_PER_THREAD <= p.B);
             if (seeded) {
                 // out += W x  /  out = W x - sub: the accumulators start from the old values (or -sub).  Only the raw
                 // loads are issued here -- 128 independent LDGs per thread that fly while the tensor core works on the
@@ -273,10 +322,16 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                 // accumulation below.  (With the scaling attached to each load, ptxas serialised the loads in small
                 // scoreboard batches: +0.7 ms per launch, round-1 measurement.)
                 const float* srow = p.accumulate ? orow : p.sub + (long long)ag * p.n_out + i;
+                if (full) {
+                    const float* sp = srow + (long long)b0 * p.o_sb;
 #pragma unroll
-                for (int c = 0; c < COLS_PER_THREAD; ++c) {
-                    const int b = b0 + c;
-                    acc[c] = (i < p.n_out && b < p.B) ? __ldcs(srow + (long long)b * p.o_sb) : 0.0f;
+                    for (int c = 0; c < COLS_PER_THREAD; ++c, sp += p.o_sb) acc[c] = __ldcs(sp);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                        const int b = b0 + c;
+                        acc[c] = (i < p.n_out && b < p.B) ? __ldcs(srow + (long long)b * p.o_sb) : 0.0f;
+                    }
                 }
             }
             const float seed1 = p.accumulate ? rescale : -rescale;
@@ -306,7 +361,42 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                 if (lane == 0) mbar_arrive_cluster(tempty_bar(buf), 0);
             }
             unsigned amax_bits = 0;
-            if (i < p.n_out) {
+            if (p.t_hi) {
+                const long long tstep = (long long)p.P * p.t_ld;
+                if (full) {
+                    long long o = ((long long)b0 * p.P + ag) * p.t_ld + i;
+#pragma unroll
+                    for (int c = 0; c < COLS_PER_THREAD; ++c, o += tstep) {
+                        const float val = acc[c] * tscale * tscale2;             // t * 2^e_t, exact
+                        const __half hv = __float2half_rn(val);
+                        p.t_hi[o] = hv;
+                        p.t_lo[o] = __float2half_rn(val - __half2float(hv));
+                        if ((c & 15) == 15) __syncwarp();                         // scheduling fence: keeps ptxas from batching all 128 conversions (spills)
+                    }
+                } else if (i < p.n_out) {
+#pragma unroll
+                    for (int c = 0; c < COLS_PER_THREAD; ++c) {
+                        const int b = b0 + c;
+                        if (b < p.B) {
+                            const float val = acc[c] * tscale * tscale2;
+                            const __half hv = __float2half_rn(val);
+                            const long long o = ((long long)b * p.P + ag) * p.t_ld + i;
+                            p.t_hi[o] = hv;
+                            p.t_lo[o] = __float2half_rn(val - __half2float(hv));
+                        }
+                    }
+                }
+            } else if (full) {
+                float* op = orow + (long long)b0 * p.o_sb;
+                float amax = 0.f;
+#pragma unroll
+                for (int c = 0; c < COLS_PER_THREAD; ++c, op += p.o_sb) {
+                    const float val = acc[c] * unscale * unscale2;
+                    *op = val;
+                    amax = fmaxf(amax, fabsf(val));
+                }
+                amax_bits = __float_as_uint(amax);
+            } else if (i < p.n_out) {
 #pragma unroll
                 for (int c = 0; c < COLS_PER_THREAD; ++c) {
                     const int b = b0 + c;
@@ -343,6 +433,7 @@ inline int pad8(int n) { return (n + 7) / 8 * 8; }
 struct Split {
     unsigned* amax;
     int* exp;
+    unsigned* l1;             // max row L1 norm (float bits), filled when the split is taken with want_l1
     __half *hi, *lo;
 };
 inline size_t split_bytes(long long rows, int n) { return 256 + ((size_t)rows * pad8(n) * 2 * 2 + 255) / 256 * 256; }
@@ -351,15 +442,16 @@ inline Split split_view(void* base, long long rows, int n) {
     Split s;
     s.amax = (unsigned*)c;
     s.exp = (int*)(c + 16);
+    s.l1 = (unsigned*)(c + 32);
     s.hi = (__half*)(c + 256);
     s.lo = s.hi + (size_t)rows * pad8(n);
     return s;
 }
 
 // x [rows][n] (row stride ld) -> split buffer (amax pass + split pass)
-inline int split_tensor(const float* x, long long rows, int n, long long ld, void* buf, cudaStream_t s) {
+inline int split_tensor(const float* x, long long rows, int n, long long ld, void* buf, cudaStream_t s, bool want_l1 = false) {
     Split v = split_view(buf, rows, n);
-    DADMM_CUDA(cudaMemsetAsync(v.amax, 0, 32, s));
+    DADMM_CUDA(cudaMemsetAsync(v.amax, 0, 64, s));
     ProfScope prof(PROF_SPLIT, s);
     if (ld == n) {
         const long long tot = rows * n;
@@ -370,9 +462,24 @@ inline int split_tensor(const float* x, long long rows, int n, long long ld, voi
     }
     DADMM_LAUNCHED();
     const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
-    split_f16_kernel<<<nblk, 256, 0, s>>>(x, rows, n, ld, pad8(n), v.amax, v.hi, v.lo, v.exp);
+    split_f16_kernel<<<nblk, 256, 0, s>>>(x, rows, n, ld, pad8(n), v.amax, v.hi, v.lo, v.exp, want_l1 ? v.l1 : nullptr);
     DADMM_LAUNCHED();
     return 0;
+}
+
+// k-blocks per tensor-core partial sum for a contraction over n_in: the longest chunk whose rounding error stays
+// below that of the exact-FMA kernel at the same n_in (rel-L2 vs fp64, random data, B200: FMA loop 2.0e-7 at 256,
+// 4.1e-7 at 1024, 5.7e-7 at 2048; this kernel 1.4e-7 with 64-k chunks, 3.7e-7 with 128-k, 8.2e-7 with 256-k).
+// DADMM_F16_KBC=<n> overrides it at run time (accuracy / speed sweeps).
+inline int kb_per_chunk(int n_in, int wanted = 0) {
+    static const int forced = [] {
+        const char* e = getenv("DADMM_F16_KBC");
+        const int x = e ? atoi(e) : 0;
+        return (x >= 1 && x <= 64) ? x : 0;
+    }();
+    if (forced) return forced;
+    if (wanted > 0) return wanted;
+    return n_in >= 1024 ? KB_PER_CHUNK : 1;
 }
 
 inline bool dims_supported(int B, int P, int n_out, int n_in) { return B >= 128 && n_out > 128 && n_in >= BKE && P >= 1; }
@@ -390,8 +497,11 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 
 // out[b,p,:] (+)= W_p x[b,p,:] from prepared operands: wprep = split of W viewed as [P*n_out][n_in],
 // xprep = split of x viewed as [B*P][n_in]
+// tprep != nullptr: first stage of a two-stage contraction -- the result leaves as the split buffer `tprep`
+// ([B*P][n_out], wprep must have been split with want_l1) and `out` is not written
 inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
-                  cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr, int fast = 0) {
+                  cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr, int fast = 0, void* tprep = nullptr,
+                  int kbc = 0) {
     tc::EncodeTiledFn enc = tc::encode_fn();
     if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
     const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
@@ -409,6 +519,12 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     p.k_blocks = ceil_div(n_in, BKE);
     p.total_tiles = P * p.m_tiles * p.n_tiles;
     p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub; p.fast = fast;
+    p.kbc = kb_per_chunk(n_in, kbc);
+    p.t_hi = p.t_lo = nullptr; p.t_ld = 0; p.t_exp = nullptr; p.w_l1 = w.l1;
+    if (tprep) {
+        const Split t = split_view(tprep, (long long)B * P, n_out);
+        p.t_hi = t.hi; p.t_lo = t.lo; p.t_ld = pad8(n_out); p.t_exp = t.exp;
+    }
     static int num_sms = [] {
         int dev = 0, n = 148;
         cudaGetDevice(&dev);
@@ -421,7 +537,7 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
         attr_set = true;
     }
     const int clusters = std::min(num_sms / 2, p.total_tiles);
-    ProfScope prof(PROF_CONTRACT_TC, s);
+    ProfScope prof(tprep ? PROF_CONTRACT_STAGE1 : PROF_CONTRACT_TC, s);
     contract_f16_kernel<<<2 * clusters, THREADS, SMEM, s>>>(mwh, mwl, mxh, mxl, p);
     DADMM_LAUNCHED();
     return 0;

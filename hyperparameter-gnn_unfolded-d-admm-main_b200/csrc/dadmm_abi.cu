@@ -399,15 +399,73 @@ static bool fused_f16(int dtype, int algo, int B, int P, int n) {
     return ra == DADMM_ALGO_TC_3XF16 || ra == DADMM_ALGO_TC_F16X1;
 }
 
+// two-stage contraction W x = F2 (F1 x) of the fused path: only where it removes a quarter of the flops or more
+// and both stages tile (DADMM_TWO_STAGE=0 forces the single-stage route, for A/B measurements)
+static bool use_factor(int dtype, int algo, int B, int P, int n, int m) {
+    static const bool enabled = [] {
+        const char* e = getenv("DADMM_TWO_STAGE");
+        return !(e && !strcmp(e, "0"));
+    }();
+    if (!enabled || m <= 0 || (m % 8) != 0 || 8LL * m > 3LL * n) return false;
+    return fused_f16(dtype, algo, B, P, n) && f16::dims_supported(B, P, m, n) && f16::dims_supported(B, P, n, m);
+}
+
+// operand-copy region at the head of the fused path's workspace
+struct FusedWs {
+    bool two;
+    size_t w1, w2, xb, tb;       // split(W) | split(F1), split(F2); split(x); split(t)
+    size_t total() const { return w1 + w2 + xb + tb; }
+};
+static FusedWs fused_ws(int dtype, int algo, int B, int P, int n, int m) {
+    FusedWs f{};
+    if (!fused_f16(dtype, algo, B, P, n)) return f;
+    f.two = use_factor(dtype, algo, B, P, n, m);
+    f.xb = f16::split_bytes((long long)B * P, n);
+    if (f.two) {
+        f.w1 = f16::split_bytes((long long)P * m, n);
+        f.w2 = f16::split_bytes((long long)P * n, m);
+        f.tb = f16::split_bytes((long long)B * P, m);
+    } else {
+        f.w1 = f16::split_bytes((long long)P * n, n);
+    }
+    return f;
+}
+static size_t unfolded_cw(int dtype, int algo, int B, int P, int n, int m) {
+    const FusedWs f = fused_ws(dtype, algo, B, P, n, m);
+    const size_t c = f.total() ? f.total() : contract_ws_bytes(dtype, algo, B, P, n, n);
+    return (c + 255) / 256 * 256;
+}
+
+// one contraction of the fused path from prepared operands: out (+)= W x (- sub)
+static int fused_contract(const FusedWs& f, char* w8, int B, int P, int n, int m, float* out, int accumulate, cudaStream_t s,
+                          unsigned* amax_out, const float* sub, int fast) {
+    char* xsp = w8 + f.w1 + f.w2;
+    if (!f.two) return f16::launch(B, P, n, n, w8, xsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast);
+    char* tsp = xsp + f.xb;
+    // partial-sum lengths: 64 k in the long first stage (1.5e-7 rel-L2), 128 k in the short, epilogue-heavy second
+    // stage (3.7e-7) -- composite 4.0e-7, the exact-FMA kernel's error for the same n; the opposite assignment is
+    // equally accurate and 0.09 ms per contraction slower (B200, cfg4)
+    if (int e = f16::launch(B, P, m, n, w8, xsp, nullptr, 0, 0, s, nullptr, nullptr, fast, tsp, 1)) return e;
+    return f16::launch(B, P, n, m, w8 + f.w1, tsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast, nullptr, 2);
+}
+static int fused_prepare(const FusedWs& f, char* w8, int P, int n, int m, const void* W, const dadmm_factor* fac, cudaStream_t s) {
+    if (!f.two) return f16::split_tensor((const float*)W, (long long)P * n, n, n, w8, s);
+    if (int e = f16::split_tensor((const float*)fac->F1, (long long)P * m, n, n, w8, s, true)) return e;
+    return f16::split_tensor((const float*)fac->F2, (long long)P * n, m, m, w8 + f.w1, s);
+}
+
 template <typename T>
 static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                             const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb, const void* y0,
+                             const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* fac,
+                             const void* Atb, const void* y0,
                              const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, int32_t* flags,
                              cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
     if (N >= (1ull << 31)) DADMM_FAIL(-1, "unfolded: B*P*n must stay below 2^31 per device (shard the batch)");
-    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const int mf = fac ? fac->m : 0;
+    const size_t cw = unfolded_cw(dtype, algo, B, P, n, mf);
+    const FusedWs fw = fused_ws(dtype, algo, B, P, n, mf);
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;
     char* a = w8 + cw;
@@ -416,12 +474,12 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     const int64_t sn = n, sPn = (int64_t)P * n;
     const size_t row = (size_t)P * 4 * es;
     const bool fused = fused_f16(dtype, algo, B, P, n);
-    const size_t wb = fused ? f16::split_bytes((long long)P * n, n) : 0;
+    const size_t wb = fw.w1 + fw.w2;
     f16::Split xs{};
     if (fused) {
         xs = f16::split_view(w8 + wb, (long long)B * P, n);
         DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
-        if (int e = f16::split_tensor((const float*)W, (long long)P * n, n, n, w8, s)) return e;
+        if (int e = fused_prepare(fw, w8, P, n, mf, W, fac, s)) return e;
         if (int e = f16::split_tensor((const float*)y0, (long long)B * P, n, n, w8 + wb, s)) return e;
     }
     for (int k = 0; k < K; ++k) {
@@ -435,7 +493,7 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         // stream (R_save[k]) -- the forward level neither reads Atb nor writes r_k; the backward rebuilds r_k from a_k'
         char* ak = (fused && R_save) ? (char*)R_save + (size_t)k * NB : a;
         if (fused) {
-            if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)ak, sPn, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1))
+            if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)ak, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1))
                 return e;
             if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
         } else {
@@ -454,12 +512,15 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
 
 template <typename T>
 static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                             const dadmm_clamps* clamps, const void* hyp, const void* Wt, const void* y0, const void* U0,
+                             const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* fac,
+                             const void* y0, const void* U0,
                              const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
                              const void* label, const double* loss_coef, void* ghyp, void* ws, cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
-    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const int mf = fac ? fac->m : 0;
+    const size_t cw = unfolded_cw(dtype, algo, B, P, n, mf);
+    const FusedWs fw = fused_ws(dtype, algo, B, P, n, mf);
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;
     char *Tb = w8 + cw, *C = Tb + NBa, *ga = C + NBa, *part = ga + NBa;
@@ -468,14 +529,14 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     const size_t row = (size_t)P * 4 * es;
     const bool with_loss = label && loss_coef;
     const bool fused = fused_f16(dtype, algo, B, P, n);
-    const size_t wb = fused ? f16::split_bytes((long long)P * n, n) : 0;
+    const size_t wb = fw.w1 + fw.w2;
     f16::Split xs{};
     DADMM_CUDA(cudaMemsetAsync(ghyp, 0, (size_t)K * row, s));
     if (fused) {
         xs = f16::split_view(w8 + wb, (long long)B * P, n);
         DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
         if (K > 1)
-            if (int e = f16::split_tensor((const float*)Wt, (long long)P * n, n, n, w8, s)) return e;
+            if (int e = fused_prepare(fw, w8, P, n, mf, Wt, fac, s)) return e;
     }
     {   // adjoint of y_K
         const long long rows = (long long)B * P;
@@ -513,7 +574,7 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         }
         if (k > 0) {
             if (fused) {
-                if (int e = f16::launch(B, P, n, n, w8, w8 + wb, (float*)Tb, sPn, 1, s, slots + (k - 1), nullptr, algo == DADMM_ALGO_TC_F16X1))
+                if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)Tb, 1, s, slots + (k - 1), nullptr, algo == DADMM_ALGO_TC_F16X1))
                     return e;
             } else {
                 if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s,
@@ -643,46 +704,54 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
     DADMM_FAIL(-1, "reduce_hyp: unknown dtype %d", dtype);
 }
 
-size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward) {
+int dadmm_unfolded_uses_factor(int dtype, int algo, int B, int P, int n, int m) { return use_factor(dtype, algo, B, P, n, m) ? 1 : 0; }
+
+size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward, int m_factor) {
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t NBa = ((size_t)B * P * n * es + 255) / 256 * 256;
-    const size_t cw = (contract_ws_bytes(dtype, algo, B, P, n, n) + 255) / 256 * 256;
+    const size_t cw = unfolded_cw(dtype, algo, B, P, n, m_factor);
     if (!backward) return cw + 3 * NBa + amax_slots_bytes(K);             // AtAy + two U ping-pong buffers + amax slots
     return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256 + amax_slots_bytes(K);   // T, C, gAtAy, partials
 }
 
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                       const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb, const void* y0,
+                       const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* factor,
+                       const void* Atb, const void* y0,
                        const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
                        int32_t* flags, dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_fwd: bad dims");
     if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
-    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0)) DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
+    if (factor && (factor->m <= 0 || !factor->F1 || !factor->F2)) DADMM_FAIL(-1, "unfolded_fwd: bad factor");
+    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0, factor ? factor->m : 0))
+        DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
     if (dtype == DADMM_F32)
-        return unfolded_fwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
+        return unfolded_fwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
                                         (cudaStream_t)stream);
     if (dtype == DADMM_F64)
-        return unfolded_fwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
+        return unfolded_fwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
                                          (cudaStream_t)stream);
     DADMM_FAIL(-1, "unfolded_fwd: unknown dtype %d", dtype);
 }
 
 int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                       const dadmm_clamps* clamps, const void* hyp, const void* Wt, const void* y0, const void* U0,
+                       const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* factor_t,
+                       const void* y0, const void* U0,
                        const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
                        const void* label, const double* loss_coef, void* ghyp, void* ws, size_t ws_bytes,
                        dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_bwd: bad dims");
     if (!clamps || !hyp || !Wt || !y0 || !U0 || !d0 || !Y || !R_save || !ghyp || !ws) DADMM_FAIL(-1, "unfolded_bwd: null pointer");
     if (K > 2 && !U_save) DADMM_FAIL(-1, "unfolded_bwd: U_save required");
-    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 1)) DADMM_FAIL(-1, "unfolded_bwd: workspace too small");
+    if (factor_t && (factor_t->m <= 0 || !factor_t->F1 || !factor_t->F2)) DADMM_FAIL(-1, "unfolded_bwd: bad factor");
+    if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 1, factor_t ? factor_t->m : 0))
+        DADMM_FAIL(-1, "unfolded_bwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
     if (dtype == DADMM_F32)
-        return unfolded_bwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, y0, U0, d0, Y, U_save, R_save, gY, label,
+        return unfolded_bwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, factor_t, y0, U0, d0, Y, U_save, R_save, gY, label,
                                         loss_coef, ghyp, ws, (cudaStream_t)stream);
     if (dtype == DADMM_F64)
-        return unfolded_bwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, y0, U0, d0, Y, U_save, R_save, gY, label,
+        return unfolded_bwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, factor_t, y0, U0, d0, Y, U_save, R_save, gY, label,
                                          loss_coef, ghyp, ws, (cudaStream_t)stream);
     DADMM_FAIL(-1, "unfolded_bwd: unknown dtype %d", dtype);
 }

@@ -14,7 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
@@ -37,6 +37,11 @@ class Hyp(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("stride_b", C.c_int64), ("stride_p", C.c_int64), ("stride_c", C.c_int64)]
 
 
+class Factor(C.Structure):
+    """W_p = F2_p F1_p, F1 [P,m,n], F2 [P,n,m] (``dadmm_factor``)."""
+    _fields_ = [("m", C.c_int32), ("F1", C.c_void_p), ("F2", C.c_void_p)]
+
+
 class DadmmError(RuntimeError):
     pass
 
@@ -48,7 +53,7 @@ def _load():
             "There is no CPU fallback for the D-ADMM hot path.")
     lib = C.CDLL(LIB_PATH)
     i32, i64, vp, dbl, sz = C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_size_t
-    GP, CP, HP = C.POINTER(Graph), C.POINTER(Clamps), C.POINTER(Hyp)
+    GP, CP, HP, FP = C.POINTER(Graph), C.POINTER(Clamps), C.POINTER(Hyp), C.POINTER(Factor)
     sigs = {
         "dadmm_abi_version": (i32, []),
         "dadmm_last_error": (C.c_char_p, []),
@@ -65,11 +70,12 @@ def _load():
                                  vp, vp, vp, vp, vp, vp]),
         "dadmm_partials_elems": (sz, [i32, i32, i32, i32]),
         "dadmm_reduce_hyp": (i32, [i32, i32, i32, i32, vp, i32, vp, i64, i64, i64, i32, vp]),
-        "dadmm_unfolded_fwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz,
+        "dadmm_unfolded_fwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp, sz,
                                      vp, vp]),
-        "dadmm_unfolded_bwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+        "dadmm_unfolded_bwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp,
                                      C.POINTER(dbl), vp, vp, sz, vp]),
-        "dadmm_unfolded_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32, i32]),
+        "dadmm_unfolded_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32, i32, i32]),
+        "dadmm_unfolded_uses_factor": (i32, [i32, i32, i32, i32, i32, i32]),
         "dadmm_loss_fwd": (i32, [i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, sz, vp]),
         "dadmm_loss_bwd": (i32, [i32, i32, i32, i32, i32, vp, vp, C.POINTER(dbl), vp, vp]),
         "dadmm_loss_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
@@ -142,7 +148,7 @@ def launch_count() -> int:
     return int(lib.dadmm_launch_count())
 
 
-PROF_KINDS = ("contract_simt", "contract_tc", "step_fwd", "step_bwd", "reduce_hyp", "loss", "split")
+PROF_KINDS = ("contract_simt", "contract_tc", "step_fwd", "step_bwd", "reduce_hyp", "loss", "split", "contract_stage1")
 
 
 def profile_enable(on: bool = True):

@@ -192,13 +192,28 @@ class Step(torch.autograd.Function):
         return gy, gU, gd, ga, None, ghyp, None, None, None
 
 
+def _factor_struct(factor, P, n, like):
+    """(Factor struct, (F1, F2)) for a factor pair, or None.  Shapes are validated here: a wrong factor would be a
+    silent wrong answer on the device."""
+    if factor is None:
+        return None
+    F1, F2 = (t.contiguous() for t in factor)
+    require_cuda(F1, F2)
+    m = F1.shape[-2]
+    if tuple(F1.shape[-3:]) != (P, m, n) or tuple(F2.shape[-3:]) != (P, n, m) or F1.dtype != like.dtype or F2.dtype != like.dtype:
+        raise _lib.DadmmError(f"factor shapes {tuple(F1.shape)}, {tuple(F2.shape)} do not describe a [P={P},n={n},n] operator")
+    return _lib.Factor(int(m), ptr(F1), ptr(F2)), (F1, F2)
+
+
 class Unfolded(torch.autograd.Function):
     """K fused iterations of model #1: hyp [K,P,4] -> Y [K,B,P,n].  Saves Y, U_k and the raw
     gradients r_k; backward runs the reverse sweep on device and returns d/d hyp only (the
     reference has no other differentiable input on this path)."""
 
     @staticmethod
-    def forward(ctx, hyp, W, Wt, Atb, y0, U0, d0, graph, clamps, algo, flags, handle):
+    def forward(ctx, hyp, W, Wt, Atb, y0, U0, d0, graph, clamps, algo, flags, handle, factor=None, factor_t=None):
+        """factor = (F1 [P,m,n], F2 [P,n,m]) with W = F2 F1, factor_t likewise for Wt (``dadmm_factor``): lets the
+        library evaluate the contraction in two stages when that is cheaper (AtA = A^T A: F1 = A, F2 = A^T)."""
         dev = require_cuda(hyp, W, Atb, y0, U0, d0)
         hyp, Atb, y0, U0, d0 = (t.contiguous() for t in (hyp, Atb, y0, U0, d0))
         K, P, _ = hyp.shape
@@ -209,16 +224,19 @@ class Unfolded(torch.autograd.Function):
         U_save = torch.empty((max(K - 1, 1), B, P, n), dtype=y0.dtype, device=dev) if need_grad else None
         R_save = torch.empty((K, B, P, n), dtype=y0.dtype, device=dev) if need_grad else None
         carr = _clamps_array(clamps)
+        fac, fac_t = _factor_struct(factor, P, n, y0), _factor_struct(factor_t, P, n, y0)
         with device_guard(dev):
-            wsb = lib.dadmm_unfolded_ws_bytes(dt, al, B, P, n, K, 0)
+            wsb = lib.dadmm_unfolded_ws_bytes(dt, al, B, P, n, K, 0, fac[0].m if fac else 0)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-            check(lib.dadmm_unfolded_fwd(dt, al, B, P, n, K, C.byref(graph.c), carr, ptr(hyp), ptr(W), ptr(Atb), ptr(y0),
+            check(lib.dadmm_unfolded_fwd(dt, al, B, P, n, K, C.byref(graph.c), carr, ptr(hyp), ptr(W),
+                                         C.byref(fac[0]) if fac else None, ptr(Atb), ptr(y0),
                                          ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(ws), wsb, ptr(flags),
                                          stream_ptr(dev)), "dadmm_unfolded_fwd")
         if need_grad:
             ctx.save_for_backward(hyp, Wt, y0, U0, d0, Y, U_save, R_save)
             ctx.graph, ctx.clamps, ctx.algo = graph, carr, al
             ctx.handle = handle
+            ctx.fac_t = fac_t            # (struct, tensors kept alive)
         return Y
 
     @staticmethod
@@ -237,14 +255,15 @@ class Unfolded(torch.autograd.Function):
         if gY is not None:
             gY = gY.contiguous()
         ghyp = torch.empty_like(hyp)
+        fac_t = ctx.fac_t
         with device_guard(dev):
-            wsb = lib.dadmm_unfolded_ws_bytes(dt, ctx.algo, B, P, n, K, 1)
+            wsb = lib.dadmm_unfolded_ws_bytes(dt, ctx.algo, B, P, n, K, 1, fac_t[0].m if fac_t else 0)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             check(lib.dadmm_unfolded_bwd(dt, ctx.algo, B, P, n, K, C.byref(ctx.graph.c), ctx.clamps, ptr(hyp), ptr(Wt),
-                                         ptr(y0), ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(gY),
+                                         C.byref(fac_t[0]) if fac_t else None, ptr(y0), ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(gY),
                                          ptr(label), coef, ptr(ghyp), ptr(ws), wsb, stream_ptr(dev)),
                   "dadmm_unfolded_bwd")
-        return (ghyp,) + (None,) * 11
+        return (ghyp,) + (None,) * 13
 
 
 def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[int] = None) -> torch.Tensor:

@@ -63,6 +63,7 @@ class DLASSO_unfolded(nn.Module):
         # knobs of the B200 path
         self.contract_algo = "auto"      # "auto" | "simt" | "tc" (tcgen05 3xTF32)
         self.check_finite = True         # one device flag read per forward (reference: 4 host syncs / iteration)
+        self.two_stage = True            # offer AtA = A^T A to the library as a factor pair (used where 4mn << 2n^2)
         self._ops = {}                   # device -> (A, AtA [P,n,n], AtA^T [P,n,n])
 
     # ------------------------------------------------------------------ operators
@@ -108,8 +109,12 @@ class DLASSO_unfolded(nn.Module):
         clamps = [DF.clamps_model1(k) for k in range(K)]
         flags = torch.zeros(K, dtype=torch.int32, device=W.device) if self.check_finite else None
         handle = DF.FusedLossHandle()
+        factor = None
+        if self.two_stage and W.dtype == torch.float32:
+            A, _, _, At = self._operators(W.device)
+            factor = (A[0], At)                          # AtA y = A^T (A y); AtA is symmetric, so the same pair serves backward
         Y = DF.Unfolded.apply(hyp, W, Wt, Atb, y0.squeeze(-1), U0.squeeze(-1), d0.squeeze(-1), graph, clamps,
-                              self.contract_algo, flags, handle)
+                              self.contract_algo, flags, handle, factor, factor)
         if flags is not None and bool(flags.any()):
             # non-finite values seen: redo the batch on the guarded path, which reproduces the reference's
             # reset / skip semantics (:55-61, :84-86, :102-104) iteration by iteration

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 2
+#define DADMM_ABI_VERSION 3
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -92,6 +92,18 @@ typedef struct dadmm_hyp {
     int64_t stride_b, stride_p, stride_c;
 } dadmm_hyp;
 
+/* Optional low-rank factorisation of the contraction operator of the fused K-iteration path:
+ *   W_p = F2_p * F1_p,   F1 [P,m,n],  F2 [P,n,m]   (contiguous, same dtype as the state)
+ * For the reference's operator AtA = A^T A (unfolded_DLASSO.py:16; rank A_p = m < n) this is F1 = A[0], F2 = A[0]^T,
+ * and W x = F2 (F1 x) costs 4mn instead of 2n^2 flops per agent (F = P*min(2n^2, 4mn)).  The
+ * library takes the two-stage route only where it pays (tensor-core path, 8m <= 3n, tile-able m); otherwise the
+ * factor is ignored and W is used.  dadmm_unfolded_uses_factor() tells which. */
+typedef struct dadmm_factor {
+    int32_t m;
+    const void* F1;
+    const void* F2;
+} dadmm_factor;
+
 int dadmm_abi_version(void);
 const char* dadmm_last_error(void);
 /* 0 when the current CUDA device is an sm_100 part this library was built for */
@@ -101,7 +113,8 @@ int64_t dadmm_launch_count(void);
 
 /* Per-kernel-kind timing for bench.py's roofline: after dadmm_profile_enable(1) every launch is bracketed
  * by CUDA events on its stream; dadmm_profile_read sums elapsed ms / launch counts per kind
- * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss, 6 operand split; arrays of 8). */
+ * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss, 6 operand split,
+ * 7 first stage of a two-stage tcgen05 contraction; arrays of 8). */
 int dadmm_profile_enable(int on);
 int dadmm_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
@@ -156,22 +169,26 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
 
 /* K iterations of model #1 (hyp [K,P,4] shared over the batch, clamps[K] on the host):
  * Y[k] = y_{k+1}; U_save[k] = U_{k+1} and R_save[k] = r_k are written when non-NULL (training).
- * W = AtA [P,n,n].  ws >= dadmm_unfolded_ws_bytes(). */
+ * W = AtA [P,n,n]; factor (may be NULL) = its factorisation.  ws >= dadmm_unfolded_ws_bytes(). */
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                       const dadmm_clamps* clamps, const void* hyp, const void* W, const void* Atb,
+                       const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* factor,
+                       const void* Atb,
                        const void* y0, const void* U0, const void* d0,
                        void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
                        int32_t* flags, dadmm_stream_t stream);
 /* Reverse sweep: gY [K,B,P,n] dense upstream gradient (may be NULL) and/or the fused loss term
- * loss_coef[k]*(Y[k]-label) (label [B,n], loss_coef host [K], both may be NULL).  Wt = AtA^T [P,n,n].
- * Writes ghyp [K,P,4]. */
+ * loss_coef[k]*(Y[k]-label) (label [B,n], loss_coef host [K], both may be NULL).  Wt = AtA^T [P,n,n];
+ * factor_t (may be NULL) factorises Wt (for the symmetric AtA: the forward's factor).  Writes ghyp [K,P,4]. */
 int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
-                       const dadmm_clamps* clamps, const void* hyp, const void* Wt,
+                       const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* factor_t,
                        const void* y0, const void* U0, const void* d0,
                        const void* Y, const void* U_save, const void* R_save,
                        const void* gY, const void* label, const double* loss_coef,
                        void* ghyp, void* ws, size_t ws_bytes, dadmm_stream_t stream);
-size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward);
+/* m_factor = factor->m of the call (0: no factor) */
+size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward, int m_factor);
+/* 1 when the fused path would evaluate the contraction in two stages for this shape and inner dimension m */
+int dadmm_unfolded_uses_factor(int dtype, int algo, int B, int P, int n, int m);
 
 /* losses[k] = sum_{b,p,i} (Y[k,b,p,i] - label[b,i])^2 / (P*B_norm*n)  (gnn_dlasso_utils.py:54-66;
  * B_norm = global batch when the batch is sharded over ranks).  ws >= dadmm_loss_ws_bytes(). */

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_header_symbols():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/dadmm.h but not exported"
     assert set(_lib.EXPORTED) == declared
-    assert _lib.lib.dadmm_abi_version() == 2
+    assert _lib.lib.dadmm_abi_version() == 3
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu():
@@ -33,8 +33,8 @@ def test_invalid_arguments_return_error_codes_without_a_gpu():
     rc = _lib.lib.dadmm_contract(0, 0, 2, 1, 4, 4, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, 0, None, 0, None)
     assert rc < 0 and b"null pointer" in _lib.lib.dadmm_last_error()
     assert _lib.lib.dadmm_partials_elems(0, 4, 5, 100) == 4 * 4 * 5 * 4
-    assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 2, 3, 8, 4, 0) >= 3 * 2 * 3 * 8 * 4
-    assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 3, 5, 51, 15, 1) % 256 == 0
+    assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 2, 3, 8, 4, 0, 0) >= 3 * 2 * 3 * 8 * 4
+    assert _lib.lib.dadmm_unfolded_ws_bytes(0, 1, 3, 5, 51, 15, 1, 0) % 256 == 0
 
 
 def test_cpu_tensors_are_rejected_loudly():

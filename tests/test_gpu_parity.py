@@ -368,6 +368,53 @@ def test_unfolded_tc_vs_simt_vs_fp64_oracle(a_scale, n):
         assert rel_l2(g_t, g_s) < max(1e-4, 50 * rel_l2(outs[algo][0][-1], outs["simt"][0][-1]))
 
 
+@pytest.mark.parametrize("m,B", [(160, 256), (136, 300)])      # m % 64 != 0: ragged last k-block; B % 256 != 0: ragged batch tile
+@pytest.mark.parametrize("a_scale", [0.1, 1.0])
+def test_unfolded_two_stage_factor_vs_fp64_oracle(a_scale, m, B):
+    """Fused path with the operator offered as the factor pair AtA = A^T A (two tensor-core stages, the first one
+    emitting its result as a scaled fp16 split): same K-step gate against the fp64 oracle as the single-stage path,
+    forward and d/d hyp, and the library really takes the two-stage route for this shape."""
+    DF, BG = _df()
+    from dadmm_b200 import _lib
+    P, n, K = 3, 512, 8
+    assert _lib.lib.dadmm_unfolded_uses_factor(0, 0, B, P, n, m) == 1
+    assert _lib.lib.dadmm_unfolded_uses_factor(0, 0, B, P, n, 256) == 0        # 8m > 3n: not worth it
+    assert _lib.lib.dadmm_unfolded_uses_factor(0, 1, B, P, n, m) == 0          # SIMT: never
+    pr = random_problem(P, n, m, B, K, seed=33, a_scale=a_scale)
+    hyp = O.hyp_table(pr["param"], torch.tensor([0.1, 0.99, 0.99, 0.99]), True)
+    A64 = pr["A"].double()
+    Y64 = O.unfolded_forward(O.atx(A64, A64), O.atx(A64, pr["b"].double()), pr["graphs"], pr["y0"].double(),
+                             pr["U0"].double(), pr["d0"].double(), hyp.double())
+    A = pr["A"].to(DEV)
+    W = DF.atx(A, A)[0].contiguous()
+    Atb = DF.atx(A, pr["b"].to(DEV)).squeeze(-1)
+    fac = (A[0].contiguous(), A[0].transpose(1, 2).contiguous())
+    graph = BG.from_graph_list(pr["graphs"], P, DEV)
+    clamps = [DF.clamps_model1(k) for k in range(K)]
+    outs = {}
+    for tag, algo, f in (("simt", "simt", None), ("one", "f16", None), ("two", "f16", fac), ("two_fast", "fast", fac)):
+        h = hyp.to(DEV).requires_grad_(True)
+        Y = DF.Unfolded.apply(h, W, W, Atb, _dev(pr["y0"]), _dev(pr["U0"]), _dev(pr["d0"]), graph, clamps, algo, None, None, f, f)
+        losses = DF.MSELoss.apply(Y, pr["label"].to(DEV), None, None)
+        losses[-1].backward()
+        outs[tag] = (Y.detach().cpu(), h.grad.cpu())
+    for k in range(K):
+        e_s, e_t = rel_l2(outs["simt"][0][k], Y64[k]), rel_l2(outs["two"][0][k], Y64[k])
+        assert e_t <= max(1e-5, 2 * e_s), (k, e_t, e_s)
+    e1, e2 = rel_l2(outs["one"][0][-1], Y64[-1]), rel_l2(outs["two"][0][-1], Y64[-1])
+    g1, g2 = rel_l2(outs["one"][1], outs["simt"][1]), rel_l2(outs["two"][1], outs["simt"][1])
+    print(f"a_scale={a_scale} m={m} B={B}: Y[K-1] vs fp64: simt={rel_l2(outs['simt'][0][-1], Y64[-1]):.2e} one-stage={e1:.2e} "
+          f"two-stage={e2:.2e}; grad vs simt: one={g1:.2e} two={g2:.2e}")
+    assert g2 < max(1e-4, 50 * rel_l2(outs["two"][0][-1], outs["simt"][0][-1]))
+    # flagged reduced-precision mode through the same two-stage route: 1e-2 class in the regime the flag is specified
+    # for (a_scale 0.1, as test_flagged_reduced_precision_mode); the ill-conditioned regime amplifies fp16 operand
+    # rounding over the K steps and is only bounded loosely
+    e_fast = rel_l2(outs["two_fast"][0][-1], Y64[-1])
+    print(f"   flagged fast mode, two-stage: Y[K-1] vs fp64 {e_fast:.2e}")
+    assert e_fast < (1e-2 if a_scale < 0.5 else 1e-1)
+    assert not torch.equal(outs["two"][0], outs["one"][0])       # really a different evaluation order
+
+
 # ------------------------------------------------------------------------------------------ fused K-loop vs single steps
 @pytest.mark.parametrize("name", MODEL1_CASES)
 def test_fused_levels_equal_chain_of_single_steps(name):
