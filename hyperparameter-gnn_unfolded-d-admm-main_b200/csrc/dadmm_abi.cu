@@ -273,14 +273,15 @@ static int level_cfg(int dtype, int B, int P, int n, int narr, int max_list, Ste
                      int acc_rows = 0) {
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), c)) return e;     // same vec/TB/nchunks as step_bwd
-    const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es + (size_t)acc_rows * c->TB * P * 32 * es;
+    const size_t scal = ((size_t)4 * P + (size_t)c->TB * P) * es;       // staged per-agent scalars (stage_scalars)
+    const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es + (size_t)acc_rows * c->TB * P * 32 * es + scal;
     const size_t lists = (size_t)c->TB * ((size_t)P + 1 + (size_t)std::max(max_list, 1)) * 4;
     if (narr > 0 && tiles + lists <= 110 * 1024) {
         *list_cap = std::max(max_list, 1);
         *smem = tiles + lists;
     } else {
         *list_cap = 0;
-        *smem = tiles;
+        *smem = tiles + (size_t)c->TB * ((size_t)P + 1) * 4;           // sPtr slot stays addressable
     }
     return 0;
 }
@@ -318,21 +319,24 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.csplit = c.nchunks;
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
     ProfScope prof(PROF_STEP_FWD, s);
-#define DADMM_LAUNCH_LFWD(VEC)                                                                  \
+#define DADMM_LAUNCH_LFWD(VEC, LEAN)                                                            \
     {                                                                                           \
-        if (int e = allow_smem(level_fwd_kernel<T, VEC>, smem)) return e;                       \
-        level_fwd_kernel<T, VEC><<<c.grid, kStepThreads, smem, s>>>(p);                         \
+        if (int e = allow_smem(level_fwd_kernel<T, VEC, LEAN>, smem)) return e;                 \
+        level_fwd_kernel<T, VEC, LEAN><<<c.grid, kStepThreads, smem, s>>>(p);                   \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
         if (c.vec == 4) {
-            DADMM_LAUNCH_LFWD(4)
+            // lean form: the fused fp16 path's configuration on full tiles (see level_fwd_kernel)
+            const bool lean = !atb && !graw && !p.hasD && (n % 128) == 0 && (B % c.TB) == 0;
+            if (lean) DADMM_LAUNCH_LFWD(4, true)
+            else DADMM_LAUNCH_LFWD(4, false)
             launched = true;
         }
     }
     if (!launched) {
-        if (c.vec == 2) DADMM_LAUNCH_LFWD(2)
-        else DADMM_LAUNCH_LFWD(1)
+        if (c.vec == 2) DADMM_LAUNCH_LFWD(2, false)
+        else DADMM_LAUNCH_LFWD(1, false)
     }
 #undef DADMM_LAUNCH_LFWD
     DADMM_LAUNCHED();
@@ -369,21 +373,24 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.csplit = level_bwd_csplit(B, c.TB, c.nchunks);
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
     ProfScope prof(PROF_STEP_BWD, s);
-#define DADMM_LAUNCH_LBWD(VEC)                                                                  \
+#define DADMM_LAUNCH_LBWD(VEC, LEAN)                                                            \
     {                                                                                           \
-        if (int e = allow_smem(level_bwd_kernel<T, VEC>, smem)) return e;                       \
-        level_bwd_kernel<T, VEC><<<c.grid, kStepThreads, smem, s>>>(p);                         \
+        if (int e = allow_smem(level_bwd_kernel<T, VEC, LEAN>, smem)) return e;                 \
+        level_bwd_kernel<T, VEC, LEAN><<<c.grid, kStepThreads, smem, s>>>(p);                   \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
         if (c.vec == 4) {
-            DADMM_LAUNCH_LBWD(4)
+            // lean form: the fused fp16 training path on full tiles, levels k >= 1 (see level_bwd_kernel)
+            const bool lean = !p.first && graw_is_residual && !p.hasD && !gY_prev && (n % 128) == 0 && (B % c.TB) == 0;
+            if (lean) DADMM_LAUNCH_LBWD(4, true)
+            else DADMM_LAUNCH_LBWD(4, false)
             launched = true;
         }
     }
     if (!launched) {
-        if (c.vec == 2) DADMM_LAUNCH_LBWD(2)
-        else DADMM_LAUNCH_LBWD(1)
+        if (c.vec == 2) DADMM_LAUNCH_LBWD(2, false)
+        else DADMM_LAUNCH_LBWD(1, false)
     }
 #undef DADMM_LAUNCH_LBWD
     DADMM_LAUNCHED();

@@ -217,6 +217,12 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
 #ifndef DADMM_LEVEL_MINB_BWD
 #define DADMM_LEVEL_MINB_BWD 3      // no prefetch: 3 -> 1.78 ms (80 regs, no spills), 4 -> 2.10 (spills)
 #endif
+#ifndef DADMM_LEVEL_MINB_FWD_LEAN
+#define DADMM_LEVEL_MINB_FWD_LEAN DADMM_LEVEL_MINB_FWD
+#endif
+#ifndef DADMM_LEVEL_MINB_BWD_LEAN
+#define DADMM_LEVEL_MINB_BWD_LEAN DADMM_LEVEL_MINB_BWD
+#endif
 
 // first two levels of warp_sum4: afterwards lane l holds the sum over lanes {l, l^8, l^16, l^24} of value (l >> 3)
 template <typename T>
@@ -231,14 +237,48 @@ __device__ __forceinline__ T warp_sum4_partial(T a, T b, T c, T d, int lane) {
     return k;
 }
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_kernel(const LevelFwdParams<T> p) {
+// sign(y) * tau as torch computes it (sign is 0 for 0 and NaN; +-1 * tau is exact): one compare, one bit merge, one select
+template <typename T>
+__device__ __forceinline__ T sign_times(T y, T tau) {
+    if constexpr (sizeof(T) == 4) return (fabsf(y) > 0.f) ? copysignf(tau, y) : 0.f;
+    else return (fabs(y) > 0.0) ? copysign(tau, y) : 0.0;
+}
+
+// Per-CTA staging of the per-agent scalars every row needs: sHyp[q] = (alpha_k, tau_k, rho_k, eta_{k-1}) and
+// sDeg[bl*P + q] = degree of agent q in the tile's problem bl (one LDS.128 + one LDS per row instead of five
+// dependent global loads)
+template <typename T>
+__device__ __forceinline__ void stage_scalars(T* sHyp, T* sDeg, int TB, int P, int B, int b0, const T* __restrict__ hyp_k,
+                                              const T* __restrict__ hyp_prev, const int32_t* __restrict__ deg,
+                                              const int32_t* __restrict__ gid) {
+    for (int q = threadIdx.x; q < P; q += blockDim.x) {
+        sHyp[q * 4 + 0] = __ldg(hyp_k + q * 4);
+        sHyp[q * 4 + 1] = __ldg(hyp_k + q * 4 + 1);
+        sHyp[q * 4 + 2] = __ldg(hyp_k + q * 4 + 2);
+        sHyp[q * 4 + 3] = hyp_prev ? __ldg(hyp_prev + q * 4 + 3) : (T)0;
+    }
+    for (int r = threadIdx.x; r < TB * P; r += blockDim.x) {
+        const int b = b0 + r / P;
+        sDeg[r] = (b < B) ? (T)__ldg(deg + (gid ? __ldg(gid + b) : 0) * P + (r % P)) : (T)0;
+    }
+}
+
+// LEAN: the configuration of the fused fp16 training/inference path on full tiles -- a already holds AtA y - Atb
+// (no Atb stream), r_k is not written, no delta clamp, n % (32 VEC) == 0 and B % TB == 0 (no lane / problem guards).
+// ncu (round 1) showed the generic form executing 366 straight-line instructions per 128-unknown row segment, a
+// third of them guards, zero-fills and NaN-propagating select clamps; the lean form keeps the arithmetic (same
+// operations, same order, same rounding) and drops the rest.  Non-finite inputs are caught through r_k alone: a NaN/Inf
+// in y_k reaches AtA y_k, one in U_k reaches U_k deg (0 * Inf = NaN), and any hit re-runs the batch on the guarded path.
+template <typename T, int VEC, bool LEAN>
+__global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_FWD_LEAN : DADMM_LEVEL_MINB_FWD) level_fwd_kernel(const LevelFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
     const int P = p.P, R = p.TB * P;
     unsigned char* S0 = smem_raw;                                              // y_k tile [R][CH]
-    int32_t* sPtr = reinterpret_cast<int32_t*>(S0 + (size_t)R * CH * sizeof(T));
+    T* sHyp = reinterpret_cast<T*>(S0 + (p.first ? (size_t)0 : (size_t)R * CH * sizeof(T)));
+    T* sDeg = sHyp + 4 * P;
+    int32_t* sPtr = reinterpret_cast<int32_t*>(sDeg + R);
     int32_t* sIdx = sPtr + p.TB * (P + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int lane_bytes = lane * VEC * (int)sizeof(T);
@@ -252,7 +292,7 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     __shared__ float sAlpha[32];
 
     // scale of the fused fp16 split of y_{k+1} (identical in every CTA)
-    float sc1 = 1.f, sc2 = 1.f;
+    float sc = 1.f;
     bool do_split = false;
     if constexpr (sizeof(T) == 4) {
         do_split = p.sp.hi != nullptr;
@@ -263,20 +303,23 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
                 bound = fminf(bound, __uint_as_float(__ldg(p.sp.amax_in)) + amax_alpha * (float)p.G);
             }
             const int e = split_exponent(bound);
-            sc1 = pow2_of(e / 2);
-            sc2 = pow2_of(e - e / 2);
+            sc = pow2_of(e / 2) * pow2_of(e - e / 2);    // |e| <= 115: a normal float, the product is exact
             if (blockIdx.x == 0 && threadIdx.x == 0) *p.sp.exp = e;
         }
     }
     unsigned amax_bits = 0;
+    float amax_f = 0.f;
 
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
+    if (first) __syncthreads();                          // (the tile-load barrier below covers the other levels)
     T nonfinite = (T)0;
+    const T nG = -p.G, nV = -p.V;
 
     for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
     const int i = chunk * CH + lane * VEC;
-    const bool act_i = i < p.n;
+    const bool act_i = LEAN || i < p.n;
     if (!first) {
         if (chunk != chunk_begin) __syncthreads();      // rows of the previous chunk are still being read
         for (int bl = 0; bl < p.TB; ++bl) {
@@ -284,93 +327,96 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
             const T* src = p.y + (((unsigned)b * P) * p.n + i);
             for (int pp = warp; pp < P; pp += nwarps) {
                 V v = vzero<T, VEC>();
-                if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+                if (LEAN || (act_i && b < p.B)) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
                 *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
             }
         }
         __syncthreads();
     }
 
-    struct Row { V a, atb, U, y, d; };
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
-        if (b >= p.B) break;
+        if (!LEAN && b >= p.B) break;
         const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
-        const int node0 = (p.gid ? __ldg(p.gid + b) : 0) * P;
         const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
-        auto issue = [&](int pp, Row& L) {
-            L.a = L.atb = L.U = L.y = L.d = vzero<T, VEC>();
-            if (pp < P && act_i) {
-                const unsigned off = base + (unsigned)pp * p.n;
-                L.a = ld_stream<T, VEC>(p.a + off);
-                if (p.atb) L.atb = ld_stream<T, VEC>(p.atb + off);
-                L.U = ld_stream<T, VEC>(p.U_in + off);
+        for (int pp = warp; pp < P; pp += nwarps) {
+            const unsigned off = base + (unsigned)pp * p.n;
+            V av, atbv, Uv, yv, dv;
+            if constexpr (LEAN) {
+                av = ld_stream<T, VEC>(p.a + off);
+                Uv = ld_stream<T, VEC>(p.U_in + off);
                 if (first) {
-                    L.y = ld_vec<T, VEC>(p.y + off);
-                    L.d = ld_stream<T, VEC>(p.d0 + off);
+                    yv = ld_vec<T, VEC>(p.y + off);
+                    dv = ld_stream<T, VEC>(p.d0 + off);
+                }
+            } else {
+                av = atbv = Uv = yv = dv = vzero<T, VEC>();
+                if (act_i) {
+                    av = ld_stream<T, VEC>(p.a + off);
+                    if (p.atb) atbv = ld_stream<T, VEC>(p.atb + off);
+                    Uv = ld_stream<T, VEC>(p.U_in + off);
+                    if (first) {
+                        yv = ld_vec<T, VEC>(p.y + off);
+                        dv = ld_stream<T, VEC>(p.d0 + off);
+                    }
                 }
             }
-        };
-        Row cur, nxt;
-#if DADMM_LEVEL_FWD_PREFETCH
-        issue(warp, cur);
-#endif
-        for (int pp = warp; pp < P; pp += nwarps) {
-#if DADMM_LEVEL_FWD_PREFETCH
-            issue(pp + nwarps, nxt);
-#else
-            issue(pp, cur);
-#endif
-            const unsigned off = base + (unsigned)pp * p.n;
-            const T alpha = __ldg(p.hyp_k + pp * 4), tau = __ldg(p.hyp_k + pp * 4 + 1), rho = __ldg(p.hyp_k + pp * 4 + 2);
-            const T dg = (T)__ldg(p.deg + node0 + pp);
-            V yv = cur.y, dv = cur.d, Uv = cur.U;
+            const T alpha = sHyp[pp * 4], tau = sHyp[pp * 4 + 1], rho = sHyp[pp * 4 + 2];
+            const T dg = sDeg[bl * P + pp];
             if (!first) {
                 yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
                 dv = lap_events<T, VEC>(tile, yv, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
-                const T eta_prev = __ldg(p.hyp_prev + pp * 4 + 3);
+                const T eta_prev = sHyp[pp * 4 + 3];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    if (p.hasD) dv.v[v] = clamp_sym(dv.v[v], p.D);
-                    Uv.v[v] = clamp_sym(add_rn(Uv.v[v], mul_rn(dv.v[v], eta_prev)), p.Uc_prev);
+                    if constexpr (!LEAN) {
+                        if (p.hasD) dv.v[v] = clamp_sym(dv.v[v], p.D);
+                        Uv.v[v] = clamp_sym(add_rn(Uv.v[v], mul_rn(dv.v[v], eta_prev)), p.Uc_prev);
+                    } else {
+                        Uv.v[v] = fmin(fmax(add_rn(Uv.v[v], mul_rn(dv.v[v], eta_prev)), -p.Uc_prev), p.Uc_prev);
+                    }
                 }
             }
             V yn, rv;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const T y = yv.v[v], U = Uv.v[v];
-                T rr = p.atb ? sub_rn(cur.a.v[v], cur.atb.v[v]) : cur.a.v[v];     // a already holds AtA y - Atb in the fused path
-                rr = add_rn(rr, mul_rn(sign_of(y), tau));
+                T rr = av.v[v];                                            // the fused path's a already holds AtA y - Atb
+                if constexpr (!LEAN) {
+                    if (p.atb) rr = sub_rn(rr, atbv.v[v]);
+                }
+                rr = add_rn(rr, sign_times(y, tau));
                 rr = add_rn(rr, mul_rn(U, dg));
                 rr = add_rn(rr, mul_rn(dv.v[v], rho));
                 // min/max clamps: identical to torch.clamp for finite values; a NaN would be swallowed, so the raw
                 // gradient joins the non-finite accumulator below (0*x is NaN iff x is Inf/NaN) and any hit sends the
                 // batch to the guarded per-iteration path (reference guards :55-61,84-86,102-104)
-                const T g = fmin(fmax(rr, -p.G), p.G);
-                const T z = fmin(fmax(sub_rn(y, mul_rn(alpha, g)), -p.V), p.V);
+                const T g = fmin(fmax(rr, nG), p.G);
+                const T z = fmin(fmax(sub_rn(y, mul_rn(alpha, g)), nV), p.V);
                 rv.v[v] = rr;
                 yn.v[v] = z;
-                nonfinite = fma(y, (T)0, fma(U, (T)0, fma(rr, (T)0, nonfinite)));
+                if constexpr (LEAN) nonfinite = fma(rr, (T)0, nonfinite);
+                else nonfinite = fma(y, (T)0, fma(U, (T)0, fma(rr, (T)0, nonfinite)));
             }
             if (act_i) {
                 st_vec<T, VEC>(p.y_next + off, yn);
                 if (p.U_out && !first) st_stream<T, VEC>(p.U_out + off, Uv);
-                if (p.graw) st_stream<T, VEC>(p.graw + off, rv);
+                if constexpr (!LEAN) {
+                    if (p.graw) st_stream<T, VEC>(p.graw + off, rv);
+                }
                 if constexpr (sizeof(T) == 4) {
-                    if (do_split) store_split<VEC>(p.sp, off, yn, sc1, sc2);
+                    if (do_split) store_split<VEC>(p.sp, off, yn, sc, 1.f);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) amax_bits = max(amax_bits, __float_as_uint(fabsf(yn.v[v])));
+                    for (int v = 0; v < VEC; ++v) amax_f = fmaxf(amax_f, fabsf(yn.v[v]));
                 }
             }
-#if DADMM_LEVEL_FWD_PREFETCH
-            cur = nxt;
-#endif
         }
     }
     }   // chunk loop
     if constexpr (sizeof(T) == 4) {
+        amax_bits = __float_as_uint(amax_f);
         if (p.sp.amax_out) publish_amax(amax_bits, p.sp.amax_out, sAmax);
     }
     if (p.flags) {
@@ -381,8 +427,14 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_FWD) level_fwd_
     }
 }
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_kernel(const LevelBwdParams<T> p) {
+// LEAN: the fused fp16 training path on full tiles, levels k >= 1 -- the saved stream is the residual AtA y - Atb, no
+// delta clamp, no dense upstream gradient (the loss term arrives as coef * (y - label)), n % (32 VEC) == 0 and
+// B % TB == 0.  Same arithmetic as the generic form; masks are |x| <= c compares (identical to torch's closed
+// interval, false for NaN), clamps are min/max, the per-agent scalars come from shared memory.  ncu (round 1): the
+// generic form executes ~600 straight-line instructions per 128-unknown row segment, two thirds of them guards,
+// zero-fills and select chains.
+template <typename T, int VEC, bool LEAN>
+__global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN : DADMM_LEVEL_MINB_BWD) level_bwd_kernel(const LevelBwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
@@ -390,7 +442,9 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     unsigned char* S0 = smem_raw;                                   // y_k tile
     unsigned char* S1 = S0 + (size_t)R * CH * sizeof(T);            // adjoint of the unclamped 2L y_k
     T* sAcc = reinterpret_cast<T*>(S1 + (size_t)R * CH * sizeof(T));   // [R][32]: per-row, per-lane partial sums of d/d hyp
-    int32_t* sPtr = reinterpret_cast<int32_t*>(sAcc + (size_t)R * 32);
+    T* sHyp = sAcc + (size_t)R * 32;                                // staged per-agent scalars (stage_scalars)
+    T* sDeg = sHyp + 4 * P;
+    int32_t* sPtr = reinterpret_cast<int32_t*>(sDeg + R);
     int32_t* sIdx = sPtr + p.TB * (P + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int lane_bytes = lane * VEC * (int)sizeof(T);
@@ -422,23 +476,88 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
     for (int r = threadIdx.x; r < R * 32; r += blockDim.x) sAcc[r] = (T)0;
+    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
+    const T nG = -p.G, nUc = -p.Uc_prev;
 
     for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
     const int i = chunk * CH + lane * VEC;
-    const bool act_i = i < p.n;
+    const bool act_i = LEAN || i < p.n;
     if (chunk != chunk_begin) __syncthreads();          // the previous chunk's last phase still reads the tiles
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
         const T* src = p.y + (((unsigned)b * P) * p.n + i);
         for (int pp = warp; pp < P; pp += nwarps) {
             V v = vzero<T, VEC>();
-            if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+            if (LEAN || (act_i && b < p.B)) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
             *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
             if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
         }
     }
     __syncthreads();
 
+    if constexpr (LEAN) {
+    for (int bl = 0; bl < p.TB; ++bl) {
+        const int b = b0 + bl;
+        const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
+        const unsigned char* tile = S0 + (size_t)bl * P * CH * sizeof(T);
+        unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
+        const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
+        const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
+        V labv = vzero<T, VEC>();
+        if (p.label) labv = ld_vec<T, VEC>(p.label + ((unsigned)b * p.n + i));
+        for (int pp = warp; pp < P; pp += nwarps) {
+            const unsigned off = base + (unsigned)pp * p.n;
+            const V tv = ld_vec<T, VEC>(p.Tb + off);
+            const V rv = ld_stream<T, VEC>(p.graw + off);
+            const V uv = ld_stream<T, VEC>(p.U_prev + off);
+            V cv = vzero<T, VEC>();
+            if (!top) cv = ld_vec<T, VEC>(p.C + off);
+            const T alpha = sHyp[pp * 4], tau = sHyp[pp * 4 + 1], rho = sHyp[pp * 4 + 2], eta_prev = sHyp[pp * 4 + 3];
+            const T dg = sDeg[bl * P + pp];
+            const V yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
+            const V draw = lap_adj<T, VEC>(tile, yv, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
+            V o_ga, o_c, o_dir, o_db;
+            T pa = (T)0, pt = (T)0, pr = (T)0, pe = (T)0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const T y = yv.v[v], d = draw.v[v];
+                // r_k = (AtA y - Atb) + sign(y) tau + U_k deg + d_k rho with U_k = clamp(U_{k-1} + d_k eta_{k-1})
+                const T w = add_rn(uv.v[v], mul_rn(d, eta_prev));
+                const T Uk = fmin(fmax(w, nUc), p.Uc_prev);
+                const T sg = sign_times(y, (T)1);
+                T rr = add_rn(rv.v[v], mul_rn(sg, tau));
+                rr = add_rn(rr, mul_rn(Uk, dg));
+                rr = add_rn(rr, mul_rn(d, rho));
+                const T g = fmin(fmax(rr, nG), p.G);
+                const T z = sub_rn(y, mul_rn(alpha, g));
+                const T zb = (fabs(z) <= p.V) ? tv.v[v] : (T)0;
+                pa -= zb * g;
+                const T rb = (fabs(rr) <= p.G) ? (-alpha * zb) : (T)0;
+                pt += rb * sg;
+                pr += rb * d;
+                o_ga.v[v] = rb;
+                const T uk = cv.v[v] + dg * rb;
+                const T um = (fabs(w) <= p.Uc_prev) ? uk : (T)0;
+                pe += um * d;
+                o_c.v[v] = um;
+                o_db.v[v] = rho * rb + eta_prev * um;
+                T dir = zb;
+                if (p.label) dir += p.coef_prev * (y - labv.v[v]);
+                o_dir.v[v] = dir;
+            }
+            *reinterpret_cast<V*>(tile1 + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes) = o_db;
+            if constexpr (sizeof(T) == 4) {
+                if (do_split) store_split<VEC>(p.sp, off, o_ga, sc1, sc2);
+                else st_vec<T, VEC>(p.ga + off, o_ga);
+            } else {
+                st_vec<T, VEC>(p.ga + off, o_ga);
+            }
+            st_vec<T, VEC>(p.C + off, o_c);
+            st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
+            sAcc[(bl * P + pp) * 32 + lane] += warp_sum4_partial(pa, pt, pr, pe, lane);
+        }
+    }
+    } else {
     struct Row { V t, c, r, u, d, g, l; };
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
@@ -544,11 +663,12 @@ __global__ void __launch_bounds__(kStepThreads, DADMM_LEVEL_MINB_BWD) level_bwd_
 #endif
         }
     }
+    }   // generic form
     if (!first) {
     __syncthreads();
     for (int bl = 0; bl < p.TB; ++bl) {
         const int b = b0 + bl;
-        if (b >= p.B) break;
+        if (!LEAN && b >= p.B) break;
         const unsigned base = ((unsigned)b * P) * p.n + i;          // 32-bit element offsets: B*P*n < 2^31 (host-checked)
         const unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
