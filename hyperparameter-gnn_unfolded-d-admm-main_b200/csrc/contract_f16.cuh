@@ -159,6 +159,7 @@ struct Params {
     int t_ld;
     int* t_exp;                    // device: exponent of the t split (written by one thread)
     const unsigned* w_l1;          // device: max row L1 norm of the operator, float bits
+    const unsigned* sub_amax;      // device, with t_hi && sub: max |sub| bits (joins the bound of t = F1 x - sub)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -296,7 +297,8 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             // |x| 2^exp_x < 2^14 by construction of every split, so |t| < 2^(14 - exp_x) * L1(F1); 1 % covers the fp32
             // rounding of the L1 sum
             const int ex = max(-112, min(126, 14 - __ldg(p.exp_x)));
-            const float bound = pow2f(ex) * (__uint_as_float(__ldg(p.w_l1)) * 1.01f);
+            float bound = pow2f(ex) * (__uint_as_float(__ldg(p.w_l1)) * 1.01f);
+            if (p.sub) bound += __uint_as_float(__ldg(p.sub_amax));
             const int et = scale_exponent(__float_as_uint(bound));
             const int ts = et + es;                                   // accumulators hold t * 2^(exp_w + exp_x)
             tscale = pow2f(ts / 2);
@@ -482,6 +484,16 @@ inline int kb_per_chunk(int n_in, int wanted = 0) {
     return n_in >= 1024 ? KB_PER_CHUNK : 1;
 }
 
+// max |x| bits of a contiguous tensor into *out (zeroed here)
+inline int amax_tensor(const float* x, long long tot, unsigned* out, cudaStream_t s) {
+    DADMM_CUDA(cudaMemsetAsync(out, 0, 4, s));
+    ProfScope prof(PROF_SPLIT, s);
+    const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(tot, 1024));
+    amax_kernel<<<nblk, 256, 0, s>>>(x, tot, out);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
 inline bool dims_supported(int B, int P, int n_out, int n_in) { return B >= 128 && n_out > 128 && n_in >= BKE && P >= 1; }
 
 inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
@@ -501,7 +513,7 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 // ([B*P][n_out], wprep must have been split with want_l1) and `out` is not written
 inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
                   cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr, int fast = 0, void* tprep = nullptr,
-                  int kbc = 0) {
+                  int kbc = 0, const unsigned* sub_amax = nullptr) {
     tc::EncodeTiledFn enc = tc::encode_fn();
     if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
     const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
@@ -520,7 +532,8 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     p.total_tiles = P * p.m_tiles * p.n_tiles;
     p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub; p.fast = fast;
     p.kbc = kb_per_chunk(n_in, kbc);
-    p.t_hi = p.t_lo = nullptr; p.t_ld = 0; p.t_exp = nullptr; p.w_l1 = w.l1;
+    p.t_hi = p.t_lo = nullptr; p.t_ld = 0; p.t_exp = nullptr; p.w_l1 = w.l1; p.sub_amax = sub_amax;
+    if (tprep && sub && !sub_amax) DADMM_FAIL(-1, "contract_f16: a first stage with a subtracted term needs its max |.|");
     if (tprep) {
         const Split t = split_view(tprep, (long long)B * P, n_out);
         p.t_hi = t.hi; p.t_lo = t.lo; p.t_ld = pad8(n_out); p.t_exp = t.exp;

@@ -443,17 +443,20 @@ static size_t unfolded_cw(int dtype, int algo, int B, int P, int n, int m) {
     return (c + 255) / 256 * 256;
 }
 
-// one contraction of the fused path from prepared operands: out (+)= W x (- sub)
+// one contraction of the fused path from prepared operands: out (+)= W x (- sub); with `rhs` (two-stage only) the
+// subtracted term enters the first stage instead: out = F2 (F1 x - rhs)
 static int fused_contract(const FusedWs& f, char* w8, int B, int P, int n, int m, float* out, int accumulate, cudaStream_t s,
-                          unsigned* amax_out, const float* sub, int fast) {
+                          unsigned* amax_out, const float* sub, int fast, const float* rhs = nullptr) {
     char* xsp = w8 + f.w1 + f.w2;
     if (!f.two) return f16::launch(B, P, n, n, w8, xsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast);
     char* tsp = xsp + f.xb;
+    const unsigned* rhs_amax = (const unsigned*)(tsp + 48);       // spare scalar slot of the t split header
     // partial-sum lengths: 64 k in the long first stage (1.5e-7 rel-L2), 128 k in the short, epilogue-heavy second
     // stage (3.7e-7) -- composite 4.0e-7, the exact-FMA kernel's error for the same n; the opposite assignment is
     // equally accurate and 0.09 ms per contraction slower (B200, cfg4)
-    if (int e = f16::launch(B, P, m, n, w8, xsp, nullptr, 0, 0, s, nullptr, nullptr, fast, tsp, 1)) return e;
-    return f16::launch(B, P, n, m, w8 + f.w1, tsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast, nullptr, 2);
+    if (int e = f16::launch(B, P, m, n, w8, xsp, nullptr, (int64_t)P * m, 0, s, nullptr, rhs, fast, tsp, 1, rhs ? rhs_amax : nullptr))
+        return e;
+    return f16::launch(B, P, n, m, w8 + f.w1, tsp, out, (int64_t)P * n, accumulate, s, amax_out, rhs ? nullptr : sub, fast, nullptr, 2);
 }
 static int fused_prepare(const FusedWs& f, char* w8, int P, int n, int m, const void* W, const dadmm_factor* fac, cudaStream_t s) {
     if (!f.two) return f16::split_tensor((const float*)W, (long long)P * n, n, n, w8, s);
@@ -488,7 +491,10 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
         if (int e = fused_prepare(fw, w8, P, n, mf, W, fac, s)) return e;
         if (int e = f16::split_tensor((const float*)y0, (long long)B * P, n, n, w8 + wb, s)) return e;
+        if (fw.two && fac->rhs)
+            if (int e = f16::amax_tensor((const float*)fac->rhs, (long long)B * P * mf, (unsigned*)(w8 + wb + fw.xb + 48), s)) return e;
     }
+    const float* rhs = (fused && fw.two) ? (const float*)fac->rhs : nullptr;
     for (int k = 0; k < K; ++k) {
         const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
         // U_j for j >= 1 lives in U_save[j-1] (training) or in a ping-pong buffer (inference)
@@ -500,7 +506,7 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         // stream (R_save[k]) -- the forward level neither reads Atb nor writes r_k; the backward rebuilds r_k from a_k'
         char* ak = (fused && R_save) ? (char*)R_save + (size_t)k * NB : a;
         if (fused) {
-            if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)ak, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1))
+            if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)ak, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1, rhs))
                 return e;
             if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
         } else {

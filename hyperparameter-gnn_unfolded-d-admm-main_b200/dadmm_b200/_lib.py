@@ -39,7 +39,7 @@ class Hyp(C.Structure):
 
 class Factor(C.Structure):
     """W_p = F2_p F1_p, F1 [P,m,n], F2 [P,n,m] (``dadmm_factor``)."""
-    _fields_ = [("m", C.c_int32), ("F1", C.c_void_p), ("F2", C.c_void_p)]
+    _fields_ = [("m", C.c_int32), ("F1", C.c_void_p), ("F2", C.c_void_p), ("rhs", C.c_void_p)]
 
 
 class DadmmError(RuntimeError):

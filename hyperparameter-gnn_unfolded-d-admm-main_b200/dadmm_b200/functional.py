@@ -193,16 +193,19 @@ class Step(torch.autograd.Function):
 
 
 def _factor_struct(factor, P, n, like):
-    """(Factor struct, (F1, F2)) for a factor pair, or None.  Shapes are validated here: a wrong factor would be a
-    silent wrong answer on the device."""
+    """(Factor struct, tensors kept alive) for a factor (F1, F2[, rhs]), or None.  Shapes are validated here: a wrong
+    factor would be a silent wrong answer on the device."""
     if factor is None:
         return None
-    F1, F2 = (t.contiguous() for t in factor)
-    require_cuda(F1, F2)
+    F1, F2 = (t.contiguous() for t in factor[:2])
+    rhs = factor[2].contiguous() if len(factor) > 2 and factor[2] is not None else None
+    require_cuda(F1, F2, rhs)
     m = F1.shape[-2]
     if tuple(F1.shape[-3:]) != (P, m, n) or tuple(F2.shape[-3:]) != (P, n, m) or F1.dtype != like.dtype or F2.dtype != like.dtype:
         raise _lib.DadmmError(f"factor shapes {tuple(F1.shape)}, {tuple(F2.shape)} do not describe a [P={P},n={n},n] operator")
-    return _lib.Factor(int(m), ptr(F1), ptr(F2)), (F1, F2)
+    if rhs is not None and (tuple(rhs.shape) != (like.shape[0], P, m) or rhs.dtype != like.dtype):
+        raise _lib.DadmmError(f"factor rhs shape {tuple(rhs.shape)} is not [B={like.shape[0]},P={P},m={m}]")
+    return _lib.Factor(int(m), ptr(F1), ptr(F2), ptr(rhs)), (F1, F2, rhs)
 
 
 class Unfolded(torch.autograd.Function):
@@ -212,8 +215,9 @@ class Unfolded(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hyp, W, Wt, Atb, y0, U0, d0, graph, clamps, algo, flags, handle, factor=None, factor_t=None):
-        """factor = (F1 [P,m,n], F2 [P,n,m]) with W = F2 F1, factor_t likewise for Wt (``dadmm_factor``): lets the
-        library evaluate the contraction in two stages when that is cheaper (AtA = A^T A: F1 = A, F2 = A^T)."""
+        """factor = (F1 [P,m,n], F2 [P,n,m][, rhs [B,P,m]]) with W = F2 F1 (and Atb = F2 rhs), factor_t likewise for Wt
+        (``dadmm_factor``): lets the library evaluate the contraction in two stages when that is cheaper
+        (AtA = A^T A: F1 = A, F2 = A^T, rhs = b)."""
         dev = require_cuda(hyp, W, Atb, y0, U0, d0)
         hyp, Atb, y0, U0, d0 = (t.contiguous() for t in (hyp, Atb, y0, U0, d0))
         K, P, _ = hyp.shape

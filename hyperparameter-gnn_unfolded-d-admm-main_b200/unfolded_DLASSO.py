@@ -101,20 +101,22 @@ class DLASSO_unfolded(nn.Module):
         U0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
         d0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
         table = self.seq_hyp.table(K)                                   # [K, P|1, 4]
-        Y = self._run(table, W, Wt, Atb, y0, U0, d0, graph, K)
+        Y = self._run(table, W, Wt, Atb, y0, U0, d0, graph, K, b)
         return Y, table[K - 1].unsqueeze(-1)
 
-    def _run(self, table, W, Wt, Atb, y0, U0, d0, graph, K):
+    def _run(self, table, W, Wt, Atb, y0, U0, d0, graph, K, b=None):
         hyp = table.expand(K, self.P, 4).contiguous().to(W.dtype)
         clamps = [DF.clamps_model1(k) for k in range(K)]
         flags = torch.zeros(K, dtype=torch.int32, device=W.device) if self.check_finite else None
         handle = DF.FusedLossHandle()
-        factor = None
+        factor = factor_t = None
         if self.two_stage and W.dtype == torch.float32:
             A, _, _, At = self._operators(W.device)
-            factor = (A[0], At)                          # AtA y = A^T (A y); AtA is symmetric, so the same pair serves backward
+            factor_t = (A[0], At)                        # AtA y = A^T (A y); AtA is symmetric, so the same pair serves backward
+            rhs = b.to(W.dtype).squeeze(-1) if b is not None else None
+            factor = (A[0], At, rhs)                     # forward: residual A^T (A y - b) = AtA y - Atb
         Y = DF.Unfolded.apply(hyp, W, Wt, Atb, y0.squeeze(-1), U0.squeeze(-1), d0.squeeze(-1), graph, clamps,
-                              self.contract_algo, flags, handle, factor, factor)
+                              self.contract_algo, flags, handle, factor, factor_t)
         if flags is not None and bool(flags.any()):
             # non-finite values seen: redo the batch on the guarded path, which reproduces the reference's
             # reset / skip semantics (:55-61, :84-86, :102-104) iteration by iteration

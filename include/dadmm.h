@@ -102,6 +102,10 @@ typedef struct dadmm_factor {
     int32_t m;
     const void* F1;
     const void* F2;
+    /* forward only, optional: rhs [B,P,m] with Atb = F2 rhs (the observations b, unfolded_DLASSO.py:45).  The
+     * two-stage route then forms the residual as F2 (F1 y - rhs) = AtA y - Atb in its first stage and never
+     * streams the n-long Atb.  NULL: Atb is subtracted in the second stage. */
+    const void* rhs;
 } dadmm_factor;
 
 int dadmm_abi_version(void);

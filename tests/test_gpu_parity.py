@@ -392,15 +392,21 @@ def test_unfolded_two_stage_factor_vs_fp64_oracle(a_scale, m, B):
     graph = BG.from_graph_list(pr["graphs"], P, DEV)
     clamps = [DF.clamps_model1(k) for k in range(K)]
     outs = {}
-    for tag, algo, f in (("simt", "simt", None), ("one", "f16", None), ("two", "f16", fac), ("two_fast", "fast", fac)):
+    fac_rhs = fac + (pr["b"].to(DEV).squeeze(-1).contiguous(),)        # residual formed as A^T (A y - b) in the first stage
+    for tag, algo, f in (("simt", "simt", None), ("one", "f16", None), ("two", "f16", fac), ("two_rhs", "f16", fac_rhs),
+                         ("two_fast", "fast", fac)):
         h = hyp.to(DEV).requires_grad_(True)
-        Y = DF.Unfolded.apply(h, W, W, Atb, _dev(pr["y0"]), _dev(pr["U0"]), _dev(pr["d0"]), graph, clamps, algo, None, None, f, f)
+        Y = DF.Unfolded.apply(h, W, W, Atb, _dev(pr["y0"]), _dev(pr["U0"]), _dev(pr["d0"]), graph, clamps, algo, None, None, f,
+                              None if f is None else f[:2])
         losses = DF.MSELoss.apply(Y, pr["label"].to(DEV), None, None)
         losses[-1].backward()
         outs[tag] = (Y.detach().cpu(), h.grad.cpu())
-    for k in range(K):
-        e_s, e_t = rel_l2(outs["simt"][0][k], Y64[k]), rel_l2(outs["two"][0][k], Y64[k])
-        assert e_t <= max(1e-5, 2 * e_s), (k, e_t, e_s)
+    for tag in ("two", "two_rhs"):
+        for k in range(K):
+            e_s, e_t = rel_l2(outs["simt"][0][k], Y64[k]), rel_l2(outs[tag][0][k], Y64[k])
+            assert e_t <= max(1e-5, 2 * e_s), (tag, k, e_t, e_s)
+        assert rel_l2(outs[tag][1], outs["simt"][1]) < max(1e-4, 50 * rel_l2(outs[tag][0][-1], outs["simt"][0][-1]))
+    print(f"   residual via rhs: Y[K-1] vs fp64 {rel_l2(outs['two_rhs'][0][-1], Y64[-1]):.2e}, grad vs simt {rel_l2(outs['two_rhs'][1], outs['simt'][1]):.2e}")
     e1, e2 = rel_l2(outs["one"][0][-1], Y64[-1]), rel_l2(outs["two"][0][-1], Y64[-1])
     g1, g2 = rel_l2(outs["one"][1], outs["simt"][1]), rel_l2(outs["two"][1], outs["simt"][1])
     print(f"a_scale={a_scale} m={m} B={B}: Y[K-1] vs fp64: simt={rel_l2(outs['simt'][0][-1], Y64[-1]):.2e} one-stage={e1:.2e} "
