@@ -274,7 +274,7 @@ static int level_cfg(int dtype, int B, int P, int n, int narr, int max_list, Ste
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), c)) return e;     // same vec/TB/nchunks as step_bwd
     const size_t scal = ((size_t)4 * P + (size_t)c->TB * P) * es;       // staged per-agent scalars (stage_scalars)
-    const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es + (size_t)acc_rows * c->TB * P * 32 * es + scal;
+    const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es + (size_t)acc_rows * c->TB * P * 4 * es + scal;
     const size_t lists = (size_t)c->TB * ((size_t)P + 1 + (size_t)std::max(max_list, 1)) * 4;
     if (narr > 0 && tiles + lists <= 110 * 1024) {
         *list_cap = std::max(max_list, 1);

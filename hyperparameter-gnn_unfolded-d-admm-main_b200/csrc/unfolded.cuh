@@ -221,21 +221,16 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
 #define DADMM_LEVEL_MINB_FWD_LEAN DADMM_LEVEL_MINB_FWD
 #endif
 #ifndef DADMM_LEVEL_MINB_BWD_LEAN
-#define DADMM_LEVEL_MINB_BWD_LEAN DADMM_LEVEL_MINB_BWD
+#define DADMM_LEVEL_MINB_BWD_LEAN 4  // lean form: 64 registers, ~55 KB shared memory per CTA; 3 -> 1.49 ms, 4 -> 1.45 ms
 #endif
 
-// first two levels of warp_sum4: afterwards lane l holds the sum over lanes {l, l^8, l^16, l^24} of value (l >> 3)
-template <typename T>
-__device__ __forceinline__ T warp_sum4_partial(T a, T b, T c, T d, int lane) {
-    const bool hi = lane & 16;
-    T k0 = hi ? c : a, k1 = hi ? d : b;
-    k0 += __shfl_xor_sync(0xffffffffu, hi ? a : c, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, hi ? b : d, 16);
-    const bool h8 = lane & 8;
-    T k = h8 ? k1 : k0;
-    k += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
-    return k;
+// 16-byte asynchronous global -> shared copy (LDGSTS): the tile loads of a CTA are all in flight at once and hold no
+// registers.  ncu (round 1): the register-staged form (load, wait, store, row after row) put 45 % of the backward
+// level's stall samples on the tile load and the barrier behind it.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // sign(y) * tau as torch computes it (sign is 0 for 0 and NaN; +-1 * tau is exact): one compare, one bit merge, one select
 template <typename T>
@@ -326,11 +321,17 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_FWD_LEAN
             const int b = b0 + bl;
             const T* src = p.y + (((unsigned)b * P) * p.n + i);
             for (int pp = warp; pp < P; pp += nwarps) {
-                V v = vzero<T, VEC>();
-                if (LEAN || (act_i && b < p.B)) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
-                *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
+                unsigned char* dst = S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes;
+                if constexpr (LEAN && sizeof(V) == 16) {
+                    cp_async16(dst, src + (unsigned)pp * p.n);
+                } else {
+                    V v = vzero<T, VEC>();
+                    if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+                    *reinterpret_cast<V*>(dst) = v;
+                }
             }
         }
+        if constexpr (LEAN && sizeof(V) == 16) cp_async_wait_all();
         __syncthreads();
     }
 
@@ -441,8 +442,8 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
     const int P = p.P, R = p.TB * P;
     unsigned char* S0 = smem_raw;                                   // y_k tile
     unsigned char* S1 = S0 + (size_t)R * CH * sizeof(T);            // adjoint of the unclamped 2L y_k
-    T* sAcc = reinterpret_cast<T*>(S1 + (size_t)R * CH * sizeof(T));   // [R][32]: per-row, per-lane partial sums of d/d hyp
-    T* sHyp = sAcc + (size_t)R * 32;                                // staged per-agent scalars (stage_scalars)
+    T* sAcc = reinterpret_cast<T*>(S1 + (size_t)R * CH * sizeof(T));   // [R][4]: per-row sums of d/d (alpha, tau, rho, eta_prev) over the CTA's chunks
+    T* sHyp = sAcc + (size_t)R * 4;                                // staged per-agent scalars (stage_scalars)
     T* sDeg = sHyp + 4 * P;
     int32_t* sPtr = reinterpret_cast<int32_t*>(sDeg + R);
     int32_t* sIdx = sPtr + p.TB * (P + 1);
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
 
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
-    for (int r = threadIdx.x; r < R * 32; r += blockDim.x) sAcc[r] = (T)0;
+    for (int r = threadIdx.x; r < R * 4; r += blockDim.x) sAcc[r] = (T)0;
     stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
     const T nG = -p.G, nUc = -p.Uc_prev;
 
@@ -487,12 +488,18 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
         const int b = b0 + bl;
         const T* src = p.y + (((unsigned)b * P) * p.n + i);
         for (int pp = warp; pp < P; pp += nwarps) {
-            V v = vzero<T, VEC>();
-            if (LEAN || (act_i && b < p.B)) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
-            *reinterpret_cast<V*>(S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
-            if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
+            unsigned char* dst = S0 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes;
+            if constexpr (LEAN && sizeof(V) == 16) {
+                cp_async16(dst, src + (unsigned)pp * p.n);
+            } else {
+                V v = vzero<T, VEC>();
+                if (act_i && b < p.B) v = ld_vec<T, VEC>(src + (unsigned)pp * p.n);
+                *reinterpret_cast<V*>(dst) = v;
+                if (!first && b >= p.B) *reinterpret_cast<V*>(S1 + (unsigned)(bl * P + pp) * (CH * (unsigned)sizeof(T)) + lane_bytes) = v;
+            }
         }
     }
+    if constexpr (LEAN && sizeof(V) == 16) cp_async_wait_all();
     __syncthreads();
 
     if constexpr (LEAN) {
@@ -554,7 +561,10 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
             }
             st_vec<T, VEC>(p.C + off, o_c);
             st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
-            sAcc[(bl * P + pp) * 32 + lane] += warp_sum4_partial(pa, pt, pr, pe, lane);
+            {   // lanes 0/8/16/24 end up with the row's four sums (only this warp touches the row's slots)
+                const T k4 = warp_sum4(pa, pt, pr, pe, lane);
+                if ((lane & 7) == 0) sAcc[(bl * P + pp) * 4 + (lane >> 3)] += k4;
+            }
         }
     }
     } else {
@@ -657,7 +667,10 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
                     st_vec<T, VEC>(p.Tb + off, o_dir);     // + 2L db in the last phase (same thread re-reads it)
                 }
             }
-            sAcc[(bl * P + pp) * 32 + lane] += warp_sum4_partial(pa, pt, pr, pe, lane);
+            {   // lanes 0/8/16/24 end up with the row's four sums (only this warp touches the row's slots)
+                const T k4 = warp_sum4(pa, pt, pr, pe, lane);
+                if ((lane & 7) == 0) sAcc[(bl * P + pp) * 4 + (lane >> 3)] += k4;
+            }
 #if DADMM_LEVEL_BWD_PREFETCH
             cur = nxt;
 #endif
@@ -674,11 +687,12 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
         for (int pp = warp; pp < P; pp += nwarps) {
+            const unsigned off = base + (unsigned)pp * p.n;
+            V s = vzero<T, VEC>();
+            if (act_i) s = ld_vec<T, VEC>(p.Tb + off);          // issued ahead of the shared-memory gather (an L2 hit: this thread wrote it)
             const V xq = *reinterpret_cast<const V*>(tile1 + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
             const V lt = lap_adj<T, VEC>(tile1, xq, lidx, lptr[pp], lptr[pp + 1], lane_bytes);
             if (act_i) {
-                const unsigned off = base + (unsigned)pp * p.n;
-                V s = ld_vec<T, VEC>(p.Tb + off);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) s.v[v] += lt.v[v];
                 st_vec<T, VEC>(p.Tb + off, s);
@@ -688,17 +702,11 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
     }   // !first
     }   // chunk loop
 
-    // finish the per-row sums: 8 lanes per sum -> lanes 0/8/16/24 hold (d alpha, d tau, d rho, d eta_prev)
-    for (int bl = 0; bl < p.TB; ++bl) {
-        const int b = b0 + bl;
-        if (b >= p.B) break;
-        for (int pp = warp; pp < P; pp += nwarps) {
-            T k = sAcc[(bl * P + pp) * 32 + lane];
-            k += __shfl_xor_sync(0xffffffffu, k, 4);
-            k += __shfl_xor_sync(0xffffffffu, k, 2);
-            k += __shfl_xor_sync(0xffffffffu, k, 1);
-            if ((lane & 7) == 0) p.partials[(((unsigned)cs * p.B + b) * P + pp) * 4 + (lane >> 3)] = k;
-        }
+    // one partial-sum row per CTA: (d alpha, d tau, d rho, d eta_prev) of every (problem, agent) of the tile
+    __syncthreads();
+    for (int r = threadIdx.x; r < R * 4; r += blockDim.x) {
+        const int b = b0 + (r >> 2) / P, pp = (r >> 2) % P;
+        if (b < p.B) p.partials[(((unsigned)cs * p.B + b) * P + pp) * 4 + (r & 3)] = sAcc[r];
     }
 }
 
