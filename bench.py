@@ -254,16 +254,40 @@ def run_ours(opt, w):
     loss_val = float(loss.detach())
 
     # ---- end to end through the public API with host buffers (e2e) -----------------------------------------
-    def e2e_step():
-        b = b_host.to(dev, non_blocking=True)
-        lab = label_host.to(dev, non_blocking=True)
-        return float(step(b, lab).detach())       # .item(): device->host read of the step's result
-    e2e_step()
+    # Every step's inputs start in pinned host memory and every step's loss is read back on the host, all inside the
+    # timed region.  The loader is double-buffered the way a training input pipeline is: the H2D copy of step i+1 runs
+    # on a copy stream while step i computes, and the loss of step i is read while step i+1 is queued.
+    copy_stream = torch.cuda.Stream(dev)
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            b = b_host.to(dev, non_blocking=True)
+            lab = label_host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return b, lab, ev
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream(dev)
+        nxt, pending, out = fetch(), None, []
+        for i in range(n):
+            b, lab, ev = nxt
+            cur.wait_event(ev)
+            loss = step(b, lab)
+            b.record_stream(cur)
+            lab.record_stream(cur)
+            if i + 1 < n:
+                nxt = fetch()
+            if pending is not None:
+                out.append(float(pending))       # device->host read of the previous step's result
+            pending = loss
+        out.append(float(pending))
+        return out
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(2, min(opt.steps, 5))
-    for _ in range(n_e2e):
-        e2e_step()
+    e2e_loop(n_e2e)
     barrier()
     t_e2e = max_over_ranks((time.perf_counter() - t0)) / n_e2e
 

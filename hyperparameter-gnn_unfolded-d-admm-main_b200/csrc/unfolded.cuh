@@ -217,6 +217,9 @@ __device__ __forceinline__ T warp_sum4(T a, T b, T c, T d, int lane) {
 #ifndef DADMM_LEVEL_MINB_BWD
 #define DADMM_LEVEL_MINB_BWD 3      // no prefetch: 3 -> 1.78 ms (80 regs, no spills), 4 -> 2.10 (spills)
 #endif
+#ifndef DADMM_LEVEL_BWD_LEAN_PREFETCH
+#define DADMM_LEVEL_BWD_LEAN_PREFETCH 0
+#endif
 #ifndef DADMM_LEVEL_MINB_FWD_LEAN
 #define DADMM_LEVEL_MINB_FWD_LEAN DADMM_LEVEL_MINB_FWD
 #endif
@@ -512,13 +515,29 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
         V labv = vzero<T, VEC>();
         if (p.label) labv = ld_vec<T, VEC>(p.label + ((unsigned)b * p.n + i));
+        struct In { V t, r, u, c; };
+        auto issue = [&](int q, In& L) {
+            L.c = vzero<T, VEC>();
+            if (q < P) {
+                const unsigned o = base + (unsigned)q * p.n;
+                L.t = ld_vec<T, VEC>(p.Tb + o);
+                L.r = ld_stream<T, VEC>(p.graw + o);
+                L.u = ld_stream<T, VEC>(p.U_prev + o);
+                if (!top) L.c = ld_vec<T, VEC>(p.C + o);
+            }
+        };
+        In cur, nxt;
+#if DADMM_LEVEL_BWD_LEAN_PREFETCH
+        issue(warp, cur);
+#endif
         for (int pp = warp; pp < P; pp += nwarps) {
             const unsigned off = base + (unsigned)pp * p.n;
-            const V tv = ld_vec<T, VEC>(p.Tb + off);
-            const V rv = ld_stream<T, VEC>(p.graw + off);
-            const V uv = ld_stream<T, VEC>(p.U_prev + off);
-            V cv = vzero<T, VEC>();
-            if (!top) cv = ld_vec<T, VEC>(p.C + off);
+#if DADMM_LEVEL_BWD_LEAN_PREFETCH
+            issue(pp + nwarps, nxt);            // next row's streams fly while this row computes (different rows: no aliasing)
+#else
+            issue(pp, cur);
+#endif
+            const V tv = cur.t, rv = cur.r, uv = cur.u, cv = cur.c;
             const T alpha = sHyp[pp * 4], tau = sHyp[pp * 4 + 1], rho = sHyp[pp * 4 + 2], eta_prev = sHyp[pp * 4 + 3];
             const T dg = sDeg[bl * P + pp];
             const V yv = *reinterpret_cast<const V*>(tile + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes);
@@ -565,6 +584,9 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN
                 const T k4 = warp_sum4(pa, pt, pr, pe, lane);
                 if ((lane & 7) == 0) sAcc[(bl * P + pp) * 4 + (lane >> 3)] += k4;
             }
+#if DADMM_LEVEL_BWD_LEAN_PREFETCH
+            cur = nxt;
+#endif
         }
     }
     } else {
