@@ -397,10 +397,15 @@ def main():
                     help="contraction kernel; 'fast' is the FLAGGED reduced-precision mode (fp16 operands, 1e-2 class) and is "
                          "never the default: the headline number is measured in fp32-parity mode")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="diagnostic: override the workload's global batch (the reported config then names it)")
     ap.add_argument("--one-stage", action="store_true",
                     help="keep the contraction on the explicit AtA operator (A/B switch for the two-stage form A^T (A y))")
     opt = ap.parse_args()
-    w = WORKLOADS[opt.workload]
+    w = dict(WORKLOADS[opt.workload])
+    if opt.batch:
+        w["B"] = opt.batch
+        w["desc"] += f" [diagnostic run: global batch overridden to {opt.batch}]"
     if opt.impl == "reference":
         run_reference_arm(opt, w)
     else:
