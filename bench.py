@@ -97,6 +97,9 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 5.0            # nvidia-smi can take seconds to emit its first line on a busy 8-GPU box
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -192,6 +195,7 @@ def run_ours(opt, w):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
     B_glob = w["B"]
     lo, hi = D.shard_range(B_glob, rank, world)
@@ -237,7 +241,8 @@ def run_ours(opt, w):
     for _ in range(max(opt.warmup, 3)):
         step(b_dev, label_dev)
     sampler = ClockSampler(local)
-    sampler.start()                       # nvidia-smi needs ~100 ms to emit its first line: start it before the last warm-up
+    if rank == 0:
+        sampler.start()                   # rank 0 samples its own GPU; started (and producing) before the last warm-up step
     step(b_dev, label_dev)
     barrier()
     sampler.mark()

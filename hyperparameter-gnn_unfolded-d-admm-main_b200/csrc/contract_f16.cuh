@@ -49,6 +49,7 @@ constexpr int EPI_WARP0 = 4;
 // not the MMA, paces the short chunks).
 constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;
 constexpr int COLS_PER_THREAD = 128;
+// (pairing two TMEM loads per tcgen05.wait::ld was measured and changes nothing: the drain is not latency-paced)
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------
