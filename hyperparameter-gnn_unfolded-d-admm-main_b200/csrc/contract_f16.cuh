@@ -348,6 +348,13 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                     uint32_t v[32];
                     tmem_ld32(taddr + 32u * j, v);
                     tmem_ld_wait();
+                    if (j == COLS_PER_THREAD / 32 - 1) {
+                        // the buffer is free as soon as its last columns sit in registers: release it before the adds
+                        // (the MMA of the next-but-one partial sum waits on this arrival)
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_bar(buf), 0);
+                    }
                     if (ch == 0 && !seeded) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) acc[32 * j + c] = __uint_as_float(v[c]);
@@ -359,9 +366,6 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                         for (int c = 0; c < 32; ++c) acc[32 * j + c] += __uint_as_float(v[c]);
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty_bar(buf), 0);
             }
             unsigned amax_bits = 0;
             if (p.t_hi) {

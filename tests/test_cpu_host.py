@@ -235,3 +235,57 @@ def test_shard_ranges_cover_batch():
             assert spans[0][0] == 0 and spans[-1][1] == B
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+# ------------------------------------------------------------------------------------------ graph ingestion
+def _ingestion_graphs(P):
+    import networkx as nx
+    gs = [nx.erdos_renyi_graph(P, 0.3, seed=s) for s in range(12)]
+    odd = nx.Graph()
+    odd.add_nodes_from(range(P))
+    odd.add_edges_from([(0, 1), (1, 1), (3, 2), (2, 0), (P - 1, 0)])      # a self-loop, isolated nodes, unsorted insertion order
+    empty = nx.Graph()
+    empty.add_nodes_from(range(P))
+    return gs + [odd, empty, gs[0], odd]                                   # repeated objects are de-duplicated
+
+
+@pytest.mark.parametrize("builder", ["numpy", "torch"])
+def test_vectorised_graph_ingestion_equals_per_graph_event_lists(builder):
+    """HostGraph (numpy passes) and _DeviceCSR (torch passes; on the CPU device here, on cuda in the gpu tests) against
+    the per-graph construction that mirrors unfolded_DLASSO.py:111-118,132-139 line by line."""
+    from dadmm_b200 import graph as G
+    P = 9
+    gs = _ingestion_graphs(P)
+    h = G.HostGraph(gs, P) if builder == "numpy" else G._DeviceCSR(gs, P, "cpu")
+    get = lambda a: np.asarray(a.cpu() if hasattr(a, "cpu") else a)
+    ev_ptr, ev_idx, adj_ptr, adj_idx, deg = (get(x) for x in (h.ev_ptr, h.ev_idx, h.adj_ptr, h.adj_idx, h.deg))
+    assert h.n_graphs == 14 and list(h.graph_id[-2:]) == [0, 12]
+    worst_ev = worst_adj = 0
+    for gi, g in enumerate(h.unique_graphs):
+        ev = G.event_lists(g, P)
+        worst_ev = max(worst_ev, sum(map(len, ev)))
+        nadj = 0
+        for p in range(P):
+            q = gi * P + p
+            assert ev_idx[ev_ptr[q]:ev_ptr[q + 1]].tolist() == ev[p]
+            nb = list(g.neighbors(p))
+            assert deg[q] == len(nb)
+            assert adj_idx[adj_ptr[q]:adj_ptr[q + 1]].tolist() == [j for j in nb if j != p]
+            nadj += len([j for j in nb if j != p])
+        worst_adj = max(worst_adj, nadj)
+    assert (h.max_events, h.max_adj) == (worst_ev, worst_adj)
+    assert ev_idx.dtype == np.int32 and ev_ptr.dtype == np.int32
+
+
+def test_graph_ingestion_rejects_foreign_nodes():
+    import networkx as nx
+    from dadmm_b200 import graph as G
+    g = nx.Graph()
+    g.add_nodes_from(range(4))
+    g.add_edge(0, 7)
+    with pytest.raises(ValueError, match="outside 0..3"):
+        G.HostGraph([g], 4)
+    h = nx.Graph()
+    h.add_nodes_from(range(3))
+    with pytest.raises(ValueError, match="no node 3"):
+        G.HostGraph([h], 4)

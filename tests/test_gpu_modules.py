@@ -163,3 +163,30 @@ def test_model3_module_eval_matches_golden():
         num += float((got.double() - ref.double()).pow(2).sum())
         den += float(ref.double().pow(2).sum())
     assert math.sqrt(num / den) < 1e-3, math.sqrt(num / den)
+
+
+def test_graph_ingestion_on_device_matches_host_and_prebuilt_batchgraph_is_accepted():
+    """CSR built with GPU passes (BatchGraph.from_graph_list on cuda) == the numpy construction; a BatchGraph built ahead
+    of time can be passed to forward() in place of graph_list and gives the same result."""
+    import networkx as nx
+    import unfolded_DLASSO
+    from dadmm_b200.graph import BatchGraph, HostGraph
+    g = Golden("m1_same_pergraph_P8_n48")
+    graphs = list(g.graphs) + [nx.erdos_renyi_graph(g.P, 0.4, seed=s) for s in range(40)]
+    odd = nx.Graph()
+    odd.add_nodes_from(range(g.P))
+    odd.add_edges_from([(0, 1), (1, 1), (3, 2)])
+    graphs += [odd, graphs[0]]
+    h, d = HostGraph(graphs, g.P), BatchGraph.from_graph_list(graphs, g.P, DEV)
+    for name in ("ev_ptr", "ev_idx", "adj_ptr", "adj_idx", "deg", "graph_id"):
+        assert torch.equal(getattr(d, name).cpu(), torch.from_numpy(getattr(h, name))), name
+    assert (d.max_events, d.max_adj, d.n_graphs, len(d)) == (h.max_events, h.max_adj, h.n_graphs, len(graphs))
+    model = unfolded_DLASSO.DLASSO_unfolded(g.t("A").to(DEV), _args(g, g.z["mode"].item(), g.K)).to(DEV)
+    with torch.no_grad():
+        model.seq_hyp.param.copy_(g.t("param").to(DEV))
+    b = g.t("b").to(DEV)
+    torch.manual_seed(3)
+    Y1, _ = model(b, g.graphs)
+    torch.manual_seed(3)
+    Y2, _ = model(b, BatchGraph.from_graph_list(g.graphs, g.P, DEV))
+    assert torch.equal(Y1, Y2)
