@@ -34,7 +34,7 @@ class GCNConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(int(out_channels)))
 
     def forward(self, x, adj_hat):          # x [B,P,in], adj_hat [B,P,P]
-        return torch.bmm(adj_hat, self.lin(x)) + self.bias
+        return torch.baddbmm(self.bias, adj_hat, self.lin(x))
 
 
 def normalized_adjacency(graph_list, P, device, dtype=torch.float32):
@@ -55,6 +55,21 @@ def normalized_adjacency(graph_list, P, device, dtype=torch.float32):
         mats[i] = d[:, None] * a * d[None, :]
     m = torch.from_numpy(mats).to(device=device, dtype=dtype)
     return m[torch.as_tensor(gid, device=device)] if len(uniq) > 1 else m.expand(len(graph_list), P, P)
+
+
+_EMA_CACHE = {}
+
+
+def _ema_weights(B, mom, device, dtype):
+    """[1,B] row of mom * (1-mom)^(B-1-b): the closed form of B sequential running-stat updates (b = 0 first)."""
+    key = (B, float(mom), str(device), dtype)
+    w = _EMA_CACHE.get(key)
+    if w is None:
+        w = (mom * (1.0 - mom) ** torch.arange(B - 1, -1, -1, device=device, dtype=torch.float64)).to(dtype).unsqueeze(0)
+        if len(_EMA_CACHE) > 16:
+            _EMA_CACHE.clear()
+        _EMA_CACHE[key] = w
+    return w
 
 
 class GNNHypernetwork3(nn.Module):
@@ -86,10 +101,10 @@ class GNNHypernetwork3(nn.Module):
         if bn.track_running_stats:
             with torch.no_grad():
                 mom = 0.1 if bn.momentum is None else bn.momentum
-                w = mom * (1.0 - mom) ** torch.arange(Bn - 1, -1, -1, device=x.device, dtype=x.dtype)
+                w = _ema_weights(Bn, mom, x.device, x.dtype)            # [1,B] weights of the B sequential updates (cached)
                 keep = (1.0 - mom) ** Bn
-                bn.running_mean.mul_(keep).add_((w[:, None] * mean[:, 0]).sum(0))
-                bn.running_var.mul_(keep).add_((w[:, None] * var[:, 0] * (Pn / max(Pn - 1, 1))).sum(0))
+                bn.running_mean.mul_(keep).add_((w @ mean[:, 0])[0])
+                bn.running_var.mul_(keep).add_((w @ var[:, 0])[0], alpha=Pn / max(Pn - 1, 1))
                 bn.num_batches_tracked += Bn
         return out
 
@@ -158,11 +173,13 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         h = self.fc(self.decoder(self.encoder(h, graph_list, adj_hat)))
         h = torch.clamp(torch.sigmoid(h), min=1e-4, max=0.9999)
         h = h.view(B, 4, 1 if self.DADMM_mode == 'same' else self.P, 1, 1)
-        dev = h.device
-        alpha = h[:, 0] * self.alpha_max.to(dev)
-        tau = torch.clamp(h[:, 1] * self.tau_max.to(dev), max=0.9999)
-        rho = torch.clamp(h[:, 2] * self.rho_max.to(dev), max=0.9999)
-        eta = torch.clamp(h[:, 3] * self.eta_max.to(dev), max=0.9999)
+        # the four maxima are 0-dim CPU tensors (reference attributes): as Python scalars they multiply with the same
+        # fp32 rounding and cost no host->device copy per iteration
+        am, tm, rm, em = (float(t) for t in (self.alpha_max, self.tau_max, self.rho_max, self.eta_max))
+        alpha = h[:, 0] * am
+        tau = torch.clamp(h[:, 1] * tm, max=0.9999)
+        rho = torch.clamp(h[:, 2] * rm, max=0.9999)
+        eta = torch.clamp(h[:, 3] * em, max=0.9999)
         return alpha, tau, rho, eta
 
     def forward(self, b, graph_list, training_iterations=None):

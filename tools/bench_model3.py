@@ -31,3 +31,7 @@ for _ in range(o.steps): lf = step()
 torch.cuda.synchronize(); t = (time.perf_counter() - t0) / o.steps
 print(f"model3 P=5 n=500 B={o.batch} K={o.K} hidden={o.hidden}: {1e3*t:.1f} ms/step, {o.K*o.batch/t:.0f} iter*problems/s, "
       f"loss_final={float(lf.detach()):.5f}, dadmm kernels/step={(_lib.launch_count()-n0)//o.steps}")
+_lib.profile_enable(True); torch.cuda.synchronize(); t0 = time.perf_counter(); step(); torch.cuda.synchronize(); t1 = time.perf_counter() - t0
+pr = _lib.profile_read(); _lib.profile_enable(False)
+lib_ms = sum(v[0] for v in pr.values())
+print(f"profiled step {1e3*t1:.1f} ms; libdadmm kernels {lib_ms:.1f} ms:", {k: (round(v[0], 2), v[1]) for k, v in pr.items() if v[1]})
