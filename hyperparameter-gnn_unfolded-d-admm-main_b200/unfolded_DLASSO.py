@@ -113,7 +113,7 @@ class DLASSO_unfolded(nn.Module):
         if self.two_stage and W.dtype == torch.float32:
             A, _, _, At = self._operators(W.device)
             factor_t = (A[0], At)                        # AtA y = A^T (A y); AtA is symmetric, so the same pair serves backward
-            rhs = b.to(W.dtype).squeeze(-1) if b is not None else None
+            rhs = b.to(W.dtype).squeeze(-1) if (b is not None and getattr(self, "two_stage_rhs", True)) else None
             factor = (A[0], At, rhs)                     # forward: residual A^T (A y - b) = AtA y - Atb
         Y = DF.Unfolded.apply(hyp, W, Wt, Atb, y0.squeeze(-1), U0.squeeze(-1), d0.squeeze(-1), graph, clamps,
                               self.contract_algo, flags, handle, factor, factor_t)
