@@ -176,7 +176,7 @@ def run_reference_arm(opt, w):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -195,7 +195,6 @@ def run_ours(opt, w):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
     B_glob = w["B"]
     lo, hi = D.shard_range(B_glob, rank, world)
@@ -334,7 +333,7 @@ def run_ours(opt, w):
                                 "host_cpus": os.cpu_count(),
                                 "sample": f"first {B_ref} problems of {opt.workload} (K={w['K']}), one fwd+bwd, {t:.1f} s; "
                                           "cost is linear in batch (Python loops per problem)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -391,7 +390,30 @@ def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False):
     return roof, breakdown
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line: everything any library writes to fd 1 (NCCL prints its version there) goes to stderr,
+    the JSON line goes to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
