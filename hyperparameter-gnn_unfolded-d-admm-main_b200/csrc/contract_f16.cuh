@@ -27,14 +27,24 @@ namespace f16 {
 #endif
 #if DADMM_F16_BK64
 constexpr int BKE = 64;                          // k elements per k-block (128-byte fp16 rows, SWIZZLE_128B)
-constexpr int STAGES = 3;
 #else
 constexpr int BKE = 32;                          // k elements per k-block (64-byte fp16 rows, SWIZZLE_64B)
-constexpr int STAGES = 6;
 #endif
-constexpr int TILE = 128 * BKE * 2;              // every operand tile: 128 rows x (64 | 128) B
-constexpr int STAGE = 4 * TILE;                  // A_hi | B_hi | A_lo | B_lo
-constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+// Tile geometry for a batch tile of NT columns per CTA pair (256: the default; 128: small batches, where 256-wide tiles
+// leave the last wave mostly empty -- 512 problems per GPU give 100 first-stage tiles for 74 CTA pairs).  Each CTA holds
+// its 128 operator rows and NT/2 batch rows per k-block; TMEM takes 512/NT partial-sum buffers.
+template <int NT>
+struct Geo {
+    static constexpr int XROWS = NT / 2;
+    static constexpr int WTILE = 128 * BKE * 2;              // bytes: 128 rows x (64 | 128) B
+    static constexpr int XTILE = XROWS * BKE * 2;
+    static constexpr int STAGE = 2 * WTILE + 2 * XTILE;      // W_hi | X_hi | W_lo | X_lo
+    static constexpr int STAGES = DADMM_F16_BK64 ? (NT == 256 ? 3 : 4) : (NT == 256 ? 6 : 8);
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+    static constexpr int NBUF = 512 / NT;
+    static constexpr int COLS = NT / 2;                      // accumulator columns per epilogue thread
+    static constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
 constexpr int THREADS = 384;                     // warps 0-3: TMA, MMA, (2 idle); warps 4-11: accumulate + store
 constexpr int EPI_WARP0 = 4;
 #ifndef DADMM_F16_KB_PER_CHUNK
@@ -48,9 +58,7 @@ constexpr int EPI_WARP0 = 4;
 // 64-k chunks 0.98 ms per two-stage contraction, 128-k 0.86 ms, 256-k 0.82 ms (the 128 KB TMEM drain per chunk,
 // not the MMA, paces the short chunks).
 constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;
-constexpr int COLS_PER_THREAD = 128;
 // (pairing two TMEM loads per tcgen05.wait::ld was measured and changes nothing: the drain is not latency-paced)
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------
 // operand preparation
@@ -133,12 +141,12 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t saddr) {
     return tc::umma_desc(saddr);
 #endif
 }
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -163,18 +171,22 @@ struct Params {
     const unsigned* sub_amax;      // device, with t_hi && sub: max |sub| bits (joins the bound of t = F1 x - sub)
 };
 
+template <int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Params p) {
     using namespace tc;
+    using G = Geo<NT>;
+    constexpr int STAGES = G::STAGES, STAGE = G::STAGE, WTILE = G::WTILE, XTILE = G::XTILE, NBUF = G::NBUF;
+    constexpr int COLS_PER_THREAD = G::COLS;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + STAGES * STAGE;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + NBUF + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * NBUF);
     auto stage_base = [&](int s) { return base + (uint32_t)s * STAGE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +198,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             mbar_init(full_bar(s), 1);       // leader: one expect_tx arrival, bytes from both CTAs' TMA
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NBUF; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 16);    // 8 accumulate warps per CTA x 2 CTAs (leader only)
         }
@@ -218,7 +230,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             uint32_t phase = 0;
             for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
                 const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
-                const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * 256 + (int)rank * 128;
+                const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * NT + (int)rank * G::XROWS;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t lead = full_bar(stage) & 0xFEFFFFFFu;     // same offset in the pair's leader CTA
@@ -226,16 +238,16 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
 #if defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT == 2
                     if (rank == 0) mbar_expect_tx(full_bar(stage), STAGE);      // timing experiment: W tiles only
                     tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
-                    tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
+                    tma_load_3d_pair(sb + WTILE + XTILE, &map_wl, lead, kb * BKE, i0, ag);
 #elif defined(DADMM_F16_EXPERIMENT) && DADMM_F16_EXPERIMENT == 3
                     if (rank == 0) mbar_arrive(full_bar(stage));                // timing experiment: no TMA at all
 #else
                     if (rank == 0) mbar_expect_tx(full_bar(stage), p.fast ? STAGE : 2 * STAGE);
                     tma_load_3d_pair(sb, &map_wh, lead, kb * BKE, i0, ag);
-                    tma_load_3d_pair(sb + TILE, &map_xh, lead, kb * BKE, ag, b0);
+                    tma_load_3d_pair(sb + WTILE, &map_xh, lead, kb * BKE, ag, b0);
                     if (!p.fast) {
-                        tma_load_3d_pair(sb + 2 * TILE, &map_wl, lead, kb * BKE, i0, ag);
-                        tma_load_3d_pair(sb + 3 * TILE, &map_xl, lead, kb * BKE, ag, b0);
+                        tma_load_3d_pair(sb + WTILE + XTILE, &map_wl, lead, kb * BKE, i0, ag);
+                        tma_load_3d_pair(sb + 2 * WTILE + XTILE, &map_xl, lead, kb * BKE, ag, b0);
                     }
 #endif
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -248,34 +260,34 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             int ci = 0;
             for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
                 for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
-                    const int buf = ci & 1;
-                    mbar_wait(tempty_bar(buf), ((uint32_t)(ci >> 1) & 1u) ^ 1u);
+                    const int buf = ci % NBUF;
+                    mbar_wait(tempty_bar(buf), ((uint32_t)(ci / NBUF) & 1u) ^ 1u);
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * NT;
                     const int kb_end = min(p.k_blocks, (ch + 1) * p.kbc);
                     for (int kb = ch * p.kbc; kb < kb_end; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tcgen05_fence_after();
-                        const uint32_t sa = stage_base(stage), sb = sa + TILE, sa_lo = sa + 2 * TILE, sb_lo = sa + 3 * TILE;
+                        const uint32_t sa = stage_base(stage), sb = sa + WTILE, sa_lo = sb + XTILE, sb_lo = sa_lo + WTILE;
                         const bool fresh = kb == ch * p.kbc;           // first k-block of the partial sum: accumulator starts at 0
                         if (!p.fast) {
                             // corrections first (see KB_PER_CHUNK): 2 x BKE/16 small accumulations, then BKE/16 full-size ones
 #pragma unroll
                             for (int ks = 0; ks < BKE / 16; ++ks) {
                                 const uint32_t koff = ks * 32;   // 16 fp16 = 32 bytes along K inside the swizzled row
-                                umma_f16_pair(d_tmem, tile_desc(sa_lo + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u);
-                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb_lo + koff), 1u);
+                                umma_f16_pair(d_tmem, tile_desc(sa_lo + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u, G::IDESC);
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb_lo + koff), 1u, G::IDESC);
                             }
 #pragma unroll
                             for (int ks = 0; ks < BKE / 16; ++ks) {
                                 const uint32_t koff = ks * 32;
-                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), 1u);
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), 1u, G::IDESC);
                             }
                         } else {
 #pragma unroll
                             for (int ks = 0; ks < BKE / 16; ++ks) {
                                 const uint32_t koff = ks * 32;
-                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u);
+                                umma_f16_pair(d_tmem, tile_desc(sa + koff), tile_desc(sb + koff), (!fresh || ks != 0) ? 1u : 0u, G::IDESC);
                             }
                         }
                         umma_commit_pair(empty_bar(stage));
@@ -309,7 +321,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
         int ci = 0;
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int ag = t / tiles_per_agent, r = t % tiles_per_agent;
-            const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * 256 + h * COLS_PER_THREAD;
+            const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * NT + h * COLS_PER_THREAD;
             float acc[COLS_PER_THREAD];
             const int i = i0 + q * 32 + lane;
             float* orow = p.out + (long long)ag * p.n_out + i;
@@ -339,10 +351,10 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             }
             const float seed1 = p.accumulate ? rescale : -rescale;
             for (int ch = 0; ch < n_chunks; ++ch, ++ci) {
-                const int buf = ci & 1;
-                mbar_wait(tfull_bar(buf), (uint32_t)(ci >> 1) & 1u);
+                const int buf = ci % NBUF;
+                mbar_wait(tfull_bar(buf), (uint32_t)(ci / NBUF) & 1u);
                 tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * COLS_PER_THREAD);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NT + h * COLS_PER_THREAD);
 #pragma unroll
                 for (int j = 0; j < COLS_PER_THREAD / 32; ++j) {
                     uint32_t v[32];
@@ -378,7 +390,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                         const __half hv = __float2half_rn(val);
                         p.t_hi[o] = hv;
                         p.t_lo[o] = __float2half_rn(val - __half2float(hv));
-                        if ((c & 15) == 15) __syncwarp();                         // scheduling fence: keeps ptxas from batching all 128 conversions (spills)
+                        if ((c & 15) == 15) __syncwarp();                         // scheduling fence: keeps ptxas from batching all conversions (spills)
                     }
                 } else if (i < p.n_out) {
 #pragma unroll
@@ -516,6 +528,40 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 // xprep = split of x viewed as [B*P][n_in]
 // tprep != nullptr: first stage of a two-stage contraction -- the result leaves as the split buffer `tprep`
 // ([B*P][n_out], wprep must have been split with want_l1) and `out` is not written
+// batch-tile width: 256 columns per CTA pair unless that leaves fewer than three waves of tiles (DADMM_F16_NT=128|256 forces one)
+inline int batch_tile(int B, int P, int n_out, int clusters) {
+    static const int forced = [] {
+        const char* e = getenv("DADMM_F16_NT");
+        const int x = e ? atoi(e) : 0;
+        return (x == 128 || x == 256) ? x : 0;
+    }();
+    if (forced) return forced;
+    const long long tiles256 = (long long)P * ceil_div(n_out, 256) * ceil_div(B, 256);
+    return tiles256 < 3LL * clusters ? 128 : 256;
+}
+
+template <int NT>
+inline int launch_nt(Params& p, const Split& x, int n_in, int B, int P, tc::EncodeTiledFn enc, const CUtensorMap& mwh,
+                     const CUtensorMap& mwl, int num_sms, bool stage1, cudaStream_t s) {
+    using G = Geo<NT>;
+    const cuuint64_t np = pad8(n_in);
+    CUtensorMap mxh, mxl;
+    if (int e = encode3(enc, &mxh, x.hi, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, G::XROWS)) return e;
+    if (int e = encode3(enc, &mxl, x.lo, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, G::XROWS)) return e;
+    p.n_tiles = ceil_div(B, NT);
+    p.total_tiles = P * p.m_tiles * p.n_tiles;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DADMM_CUDA(cudaFuncSetAttribute(contract_f16_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+        attr_set = true;
+    }
+    const int clusters = std::min(num_sms / 2, p.total_tiles);
+    ProfScope prof(stage1 ? PROF_CONTRACT_STAGE1 : PROF_CONTRACT_TC, s);
+    contract_f16_kernel<NT><<<2 * clusters, THREADS, G::SMEM, s>>>(mwh, mwl, mxh, mxl, p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
 inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, float* out, int64_t o_sb, int accumulate,
                   cudaStream_t s, unsigned* amax_out = nullptr, const float* sub = nullptr, int fast = 0, void* tprep = nullptr,
                   int kbc = 0, const unsigned* sub_amax = nullptr) {
@@ -523,18 +569,14 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     if (!enc) DADMM_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
     const Split w = split_view(wprep, (long long)P * n_out, n_in), x = split_view(xprep, (long long)B * P, n_in);
     const cuuint64_t np = pad8(n_in);
-    CUtensorMap mwh, mwl, mxh, mxl;
+    CUtensorMap mwh, mwl;
     if (int e = encode3(enc, &mwh, w.hi, n_in, n_out, P, np * 2, (cuuint64_t)n_out * np * 2, BKE, 128, 1)) return e;
     if (int e = encode3(enc, &mwl, w.lo, n_in, n_out, P, np * 2, (cuuint64_t)n_out * np * 2, BKE, 128, 1)) return e;
-    if (int e = encode3(enc, &mxh, x.hi, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, 128)) return e;
-    if (int e = encode3(enc, &mxl, x.lo, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, 128)) return e;
     Params p;
     p.B = B; p.P = P; p.n_out = n_out; p.n_in = n_in;
     p.out = out; p.o_sb = o_sb; p.accumulate = accumulate;
     p.m_tiles = ceil_div(n_out, 256);
-    p.n_tiles = ceil_div(B, 256);
     p.k_blocks = ceil_div(n_in, BKE);
-    p.total_tiles = P * p.m_tiles * p.n_tiles;
     p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub; p.fast = fast;
     p.kbc = kb_per_chunk(n_in, kbc);
     p.t_hi = p.t_lo = nullptr; p.t_ld = 0; p.t_exp = nullptr; p.w_l1 = w.l1; p.sub_amax = sub_amax;
@@ -549,16 +591,9 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    static bool attr_set = false;
-    if (!attr_set) {
-        DADMM_CUDA(cudaFuncSetAttribute(contract_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
-    const int clusters = std::min(num_sms / 2, p.total_tiles);
-    ProfScope prof(tprep ? PROF_CONTRACT_STAGE1 : PROF_CONTRACT_TC, s);
-    contract_f16_kernel<<<2 * clusters, THREADS, SMEM, s>>>(mwh, mwl, mxh, mxl, p);
-    DADMM_LAUNCHED();
-    return 0;
+    if (batch_tile(B, P, n_out, num_sms / 2) == 128)
+        return launch_nt<128>(p, x, n_in, B, P, enc, mwh, mwl, num_sms, tprep != nullptr, s);
+    return launch_nt<256>(p, x, n_in, B, P, enc, mwh, mwl, num_sms, tprep != nullptr, s);
 }
 
 }  // namespace f16
