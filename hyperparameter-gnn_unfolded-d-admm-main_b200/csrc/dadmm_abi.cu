@@ -314,9 +314,14 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     if (int e = level_cfg(dtype, B, P, n, p.first ? 0 : 1, g->max_events, &c, &smem, &p.list_cap)) return e;
     if (int e = check_aligned(dtype, c.vec, {y, U_in, d0, a, atb, y_next, U_out, graw})) return e;
     p.TB = c.TB;
-    // forward: one 128-unknown chunk per CTA (walking all chunks in one CTA, as the backward kernel does for its
-    // partial sums, measured 3 % slower here: 1.085 vs 1.05 ms)
-    p.csplit = c.nchunks;
+    // forward: two 128-unknown chunks per CTA (B200, cfg4, lean kernel: 1 chunk 0.940 ms, 2 -> 0.916, 4 -> 0.919, 8 -> 0.925;
+    // the neighbour lists and per-agent scalars are staged once per CTA; register prefetch of the next row: 0.98 ms).
+    // DADMM_FWD_CHUNKS_PER_CTA overrides.
+    {
+        static const int forced = [] { const char* e = getenv("DADMM_FWD_CHUNKS_PER_CTA"); return e ? atoi(e) : 0; }();
+        const int cpc = forced > 0 ? forced : 2;
+        p.csplit = std::max(1, (c.nchunks + cpc - 1) / cpc);
+    }
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
     ProfScope prof(PROF_STEP_FWD, s);
 #define DADMM_LAUNCH_LFWD(VEC, LEAN)                                                            \
