@@ -293,6 +293,15 @@ static int level_bwd_csplit(int B, int TB, int nchunks) {
     return std::max(1, std::min(nchunks, (148 * 12 + groups - 1) / groups));
 }
 
+// backward level: ten warps per CTA when that splits the tile's rows evenly and eight do not (P = 50: 1.361 -> 1.287 ms on
+// B200; DADMM_LEVEL_WARPS=8 keeps eight)
+static bool level_ten_warps(int rows) {
+    static const int forced = [] { const char* e = getenv("DADMM_LEVEL_WARPS"); return e ? atoi(e) : 0; }();
+    if (forced == 8) return false;
+    if (forced == 10) return true;
+    return (rows % 8) != 0 && (rows % 10) == 0;
+}
+
 template <typename T>
 static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, const void* y,
@@ -324,24 +333,24 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     }
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
     ProfScope prof(PROF_STEP_FWD, s);
-#define DADMM_LAUNCH_LFWD(VEC, LEAN)                                                            \
+#define DADMM_LAUNCH_LFWD(VEC, LEAN, NTHR)                                                      \
     {                                                                                           \
-        if (int e = allow_smem(level_fwd_kernel<T, VEC, LEAN>, smem)) return e;                 \
-        level_fwd_kernel<T, VEC, LEAN><<<c.grid, kStepThreads, smem, s>>>(p);                   \
+        if (int e = allow_smem(level_fwd_kernel<T, VEC, LEAN, NTHR>, smem)) return e;           \
+        level_fwd_kernel<T, VEC, LEAN, NTHR><<<c.grid, NTHR, smem, s>>>(p);                     \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
         if (c.vec == 4) {
             // lean form: the fused fp16 path's configuration on full tiles (see level_fwd_kernel)
             const bool lean = !atb && !graw && !p.hasD && (n % 128) == 0 && (B % c.TB) == 0;
-            if (lean) DADMM_LAUNCH_LFWD(4, true)
-            else DADMM_LAUNCH_LFWD(4, false)
+            if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level)
+            else DADMM_LAUNCH_LFWD(4, false, kStepThreads)
             launched = true;
         }
     }
     if (!launched) {
-        if (c.vec == 2) DADMM_LAUNCH_LFWD(2, false)
-        else DADMM_LAUNCH_LFWD(1, false)
+        if (c.vec == 2) DADMM_LAUNCH_LFWD(2, false, kStepThreads)
+        else DADMM_LAUNCH_LFWD(1, false, kStepThreads)
     }
 #undef DADMM_LAUNCH_LFWD
     DADMM_LAUNCHED();
@@ -378,24 +387,25 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.csplit = level_bwd_csplit(B, c.TB, c.nchunks);
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
     ProfScope prof(PROF_STEP_BWD, s);
-#define DADMM_LAUNCH_LBWD(VEC, LEAN)                                                            \
+#define DADMM_LAUNCH_LBWD(VEC, LEAN, NTHR)                                                      \
     {                                                                                           \
-        if (int e = allow_smem(level_bwd_kernel<T, VEC, LEAN>, smem)) return e;                 \
-        level_bwd_kernel<T, VEC, LEAN><<<c.grid, kStepThreads, smem, s>>>(p);                   \
+        if (int e = allow_smem(level_bwd_kernel<T, VEC, LEAN, NTHR>, smem)) return e;           \
+        level_bwd_kernel<T, VEC, LEAN, NTHR><<<c.grid, NTHR, smem, s>>>(p);                     \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
         if (c.vec == 4) {
             // lean form: the fused fp16 training path on full tiles, levels k >= 1 (see level_bwd_kernel)
             const bool lean = !p.first && graw_is_residual && !p.hasD && !gY_prev && (n % 128) == 0 && (B % c.TB) == 0;
-            if (lean) DADMM_LAUNCH_LBWD(4, true)
-            else DADMM_LAUNCH_LBWD(4, false)
+            if (lean && level_ten_warps(c.TB * P)) DADMM_LAUNCH_LBWD(4, true, 320)
+            else if (lean) DADMM_LAUNCH_LBWD(4, true, kStepThreads)
+            else DADMM_LAUNCH_LBWD(4, false, kStepThreads)
             launched = true;
         }
     }
     if (!launched) {
-        if (c.vec == 2) DADMM_LAUNCH_LBWD(2, false)
-        else DADMM_LAUNCH_LBWD(1, false)
+        if (c.vec == 2) DADMM_LAUNCH_LBWD(2, false, kStepThreads)
+        else DADMM_LAUNCH_LBWD(1, false, kStepThreads)
     }
 #undef DADMM_LAUNCH_LBWD
     DADMM_LAUNCHED();

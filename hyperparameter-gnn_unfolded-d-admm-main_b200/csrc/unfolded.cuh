@@ -267,8 +267,11 @@ __device__ __forceinline__ void stage_scalars(T* sHyp, T* sDeg, int TB, int P, i
 // third of them guards, zero-fills and NaN-propagating select clamps; the lean form keeps the arithmetic (same
 // operations, same order, same rounding) and drops the rest.  Non-finite inputs are caught through r_k alone: a NaN/Inf
 // in y_k reaches AtA y_k, one in U_k reaches U_k deg (0 * Inf = NaN), and any hit re-runs the batch on the guarded path.
-template <typename T, int VEC, bool LEAN>
-__global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_FWD_LEAN : DADMM_LEVEL_MINB_FWD) level_fwd_kernel(const LevelFwdParams<T> p) {
+// NTHR: threads per CTA.  One warp owns whole rows, so 8 warps split a 50-row tile (P = 50) as 7,7,6,6,6,6,6,6; ten warps
+// (320 threads) split it evenly.  Pays in the backward level (-5 %), not here (the host keeps 256 threads for this kernel).
+template <typename T, int VEC, bool LEAN, int NTHR = kStepThreads>
+__global__ void __launch_bounds__(NTHR, NTHR > kStepThreads ? DADMM_LEVEL_MINB_FWD_LEAN - 1 : (LEAN ? DADMM_LEVEL_MINB_FWD_LEAN : DADMM_LEVEL_MINB_FWD))
+level_fwd_kernel(const LevelFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
@@ -437,8 +440,9 @@ __global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_FWD_LEAN
 // interval, false for NaN), clamps are min/max, the per-agent scalars come from shared memory.  ncu (round 1): the
 // generic form executes ~600 straight-line instructions per 128-unknown row segment, two thirds of them guards,
 // zero-fills and select chains.
-template <typename T, int VEC, bool LEAN>
-__global__ void __launch_bounds__(kStepThreads, LEAN ? DADMM_LEVEL_MINB_BWD_LEAN : DADMM_LEVEL_MINB_BWD) level_bwd_kernel(const LevelBwdParams<T> p) {
+template <typename T, int VEC, bool LEAN, int NTHR = kStepThreads>
+__global__ void __launch_bounds__(NTHR, NTHR > kStepThreads ? DADMM_LEVEL_MINB_BWD_LEAN - 1 : (LEAN ? DADMM_LEVEL_MINB_BWD_LEAN : DADMM_LEVEL_MINB_BWD))
+level_bwd_kernel(const LevelBwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CH = 32 * VEC;
     using V = Vec<T, VEC>;
