@@ -324,7 +324,7 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
             const int i0 = (r % p.m_tiles) * 256 + (int)rank * 128, b0 = (r / p.m_tiles) * NT + h * COLS_PER_THREAD;
             float acc[COLS_PER_THREAD];
             const int i = i0 + q * 32 + lane;
-            float* orow = p.out + (long long)ag * p.n_out + i;
+            float* orow = p.out ? p.out + (long long)ag * p.n_out + i : nullptr;      // first stage of a two-stage call: no fp32 output
             const bool seeded = p.accumulate || p.sub != nullptr;
             // full tile: every (i, b) of this thread is in range -- no per-element predicates, addresses by pointer stepping
             // (ncu, round 1: the guarded 64-bit index form cost ~16 instructions per load and ~20 per store and made the

@@ -290,6 +290,8 @@ static int level_cfg(int dtype, int B, int P, int n, int narr, int max_list, Ste
 // batch is too small to fill the machine
 static int level_bwd_csplit(int B, int TB, int nchunks) {
     const int groups = (B + TB - 1) / TB;
+    static const int forced = [] { const char* e = getenv("DADMM_BWD_CSPLIT"); return e ? atoi(e) : 0; }();   // experiment knob
+    if (forced > 0) return std::max(1, std::min(nchunks, forced));
     return std::max(1, std::min(nchunks, (148 * 12 + groups - 1) / groups));
 }
 
@@ -306,7 +308,8 @@ template <typename T>
 static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, const void* y,
                           const void* U_in, const void* d0, const void* a, const void* atb, void* y_next, void* U_out,
-                          void* graw, int32_t* flags, const SplitOut& sp, cudaStream_t s) {
+                          void* graw, int32_t* flags, const SplitOut& sp, cudaStream_t s, void* agent_sum = nullptr,
+                          double* sq_part = nullptr, int* sums_grid = nullptr) {
     LevelFwdParams<T> p;
     p.sp = sp;
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr);
@@ -318,6 +321,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.Uc_prev = cl_prev ? (T)cl_prev->Uc : (T)0;
     p.y = (const T*)y; p.U_in = (const T*)U_in; p.d0 = (const T*)d0; p.a = (const T*)a; p.atb = (const T*)atb;
     p.y_next = (T*)y_next; p.U_out = (T*)U_out; p.graw = (T*)graw; p.flags = flags;
+    p.agent_sum = nullptr; p.sq_part = nullptr;
     StepCfg c;
     size_t smem = 0;
     if (int e = level_cfg(dtype, B, P, n, p.first ? 0 : 1, g->max_events, &c, &smem, &p.list_cap)) return e;
@@ -343,6 +347,12 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
         if (c.vec == 4) {
             // lean form: the fused fp16 path's configuration on full tiles (see level_fwd_kernel)
             const bool lean = !atb && !graw && !p.hasD && (n % 128) == 0 && (B % c.TB) == 0;
+            // label-free loss sums (dadmm_loss_sums): lean form, one problem per CTA, a tile at least as tall as the CTA has warps
+            if (lean && agent_sum && sq_part && !p.first && c.TB == 1 && P >= kStepThreads / 32) {
+                p.agent_sum = (T*)agent_sum;
+                p.sq_part = sq_part;
+                if (sums_grid) *sums_grid = c.grid;
+            }
             if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level)
             else DADMM_LAUNCH_LFWD(4, false, kStepThreads)
             launched = true;
@@ -414,6 +424,14 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
 
 static size_t amax_slots_bytes(int K) { return ((size_t)(K + 1) * 4 + 255) / 256 * 256; }
 
+// per-CTA sum-of-squares partials of the forward levels (dadmm_loss_sums): K rows of one double per CTA
+static size_t sq_part_bytes(int dtype, int B, int P, int n, int K) {
+    StepCfg c;
+    if (dtype != DADMM_F32 || step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return 0;
+    const size_t grid = (size_t)((B + c.TB - 1) / c.TB) * c.nchunks;         // upper bound of the level grid
+    return ((size_t)K * grid * sizeof(double) + 255) / 256 * 256;
+}
+
 // the fused fp16 path: operands of the contraction are produced already split by the level kernels
 static bool fused_f16(int dtype, int algo, int B, int P, int n) {
     if (dtype != DADMM_F32 || (n % 8) != 0) return false;
@@ -484,7 +502,7 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                              const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* fac,
                              const void* Atb, const void* y0,
                              const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, int32_t* flags,
-                             cudaStream_t s) {
+                             const dadmm_loss_sums* sums, cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
     if (N >= (1ull << 31)) DADMM_FAIL(-1, "unfolded: B*P*n must stay below 2^31 per device (shard the batch)");
@@ -496,6 +514,11 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     char* a = w8 + cw;
     char* pp[2] = {a + NBa, a + 2 * NBa};
     unsigned* slots = (unsigned*)(a + 3 * NBa);     // max|y_k| bits, k = 0..K
+    double* sq_part = (double*)((char*)slots + amax_slots_bytes(K));         // [K][level grid] (dadmm_loss_sums)
+    const size_t sq_row = sq_part_bytes(dtype, B, P, n, K) / sizeof(double) / (size_t)std::max(K, 1);
+    int sums_grid = 0, sums_first = K;
+    if (sums)
+        for (int k = 0; k < K; ++k) sums->valid[k] = 0;
     const int64_t sn = n, sPn = (int64_t)P * n;
     const size_t row = (size_t)P * 4 * es;
     const bool fused = fused_f16(dtype, algo, B, P, n);
@@ -532,8 +555,20 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                                       k ? (const char*)hyp + (k - 1) * row : nullptr, yk, Uin, d0, ak, fused ? nullptr : Atb,
                                       (char*)Y + (size_t)k * NB, Uout,
                                       (R_save && !fused) ? (char*)R_save + (size_t)k * NB : nullptr,
-                                      flags ? flags + k : nullptr, sp, s))
+                                      flags ? flags + k : nullptr, sp, s,
+                                      (sums && fused && sq_row) ? (char*)sums->agent_sum + (size_t)k * B * n * es : nullptr,
+                                      (sums && fused && sq_row) ? sq_part + (size_t)k * sq_row : nullptr, &sums_grid))
             return e;
+        if (sums && sums_grid > 0 && k >= 1) {        // the level produced the sums (its grid is the same for every k >= 1)
+            sums->valid[k] = 1;
+            sums_first = std::min(sums_first, k);
+        }
+    }
+    if (sums && sums_first < K) {
+        DADMM_CUDA(cudaMemsetAsync(sums->sumsq, 0, (size_t)K * sizeof(double), s));
+        ProfScope prof(PROF_LOSS, s);
+        sumsq_final_kernel<<<K - sums_first, 256, 0, s>>>(sq_part, sq_row, sums_grid, sums_first, sums->sumsq);
+        DADMM_LAUNCHED();
     }
     return 0;
 }
@@ -738,7 +773,8 @@ size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, 
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t NBa = ((size_t)B * P * n * es + 255) / 256 * 256;
     const size_t cw = unfolded_cw(dtype, algo, B, P, n, m_factor);
-    if (!backward) return cw + 3 * NBa + amax_slots_bytes(K);             // AtAy + two U ping-pong buffers + amax slots
+    if (!backward)   // AtAy + two U ping-pong buffers + amax slots + sum-of-squares partials
+        return cw + 3 * NBa + amax_slots_bytes(K) + sq_part_bytes(dtype, B, P, n, K);
     return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256 + amax_slots_bytes(K);   // T, C, gAtAy, partials
 }
 
@@ -746,19 +782,20 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
                        const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* factor,
                        const void* Atb, const void* y0,
                        const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
-                       int32_t* flags, dadmm_stream_t stream) {
+                       int32_t* flags, const dadmm_loss_sums* sums, dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_fwd: bad dims");
     if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
     if (factor && (factor->m <= 0 || !factor->F1 || !factor->F2)) DADMM_FAIL(-1, "unfolded_fwd: bad factor");
+    if (sums && (!sums->agent_sum || !sums->sumsq || !sums->valid)) DADMM_FAIL(-1, "unfolded_fwd: bad loss-sums descriptor");
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0, factor ? factor->m : 0))
         DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
     if (dtype == DADMM_F32)
         return unfolded_fwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
-                                        (cudaStream_t)stream);
+                                        sums, (cudaStream_t)stream);
     if (dtype == DADMM_F64)
         return unfolded_fwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
-                                         (cudaStream_t)stream);
+                                         sums, (cudaStream_t)stream);
     DADMM_FAIL(-1, "unfolded_fwd: unknown dtype %d", dtype);
 }
 
@@ -813,6 +850,35 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
         DADMM_LAUNCHED();
     } else {
         DADMM_FAIL(-1, "loss_fwd: unknown dtype %d", dtype);
+    }
+    return 0;
+}
+
+int dadmm_loss_from_sums(int dtype, int k0, int k1, int B, int P, int n, int64_t B_norm, const void* agent_sum,
+                         const double* sumsq, const void* label, void* losses, void* ws, size_t ws_bytes,
+                         dadmm_stream_t stream) {
+    if (k0 < 0 || k1 <= k0 || B <= 0 || P <= 0 || n <= 0 || B_norm <= 0) DADMM_FAIL(-1, "loss_from_sums: bad dims");
+    if (!agent_sum || !sumsq || !label || !losses || !ws) DADMM_FAIL(-1, "loss_from_sums: null pointer");
+    if (ws_bytes < dadmm_loss_ws_bytes(dtype, k1, B, P, n)) DADMM_FAIL(-1, "loss_from_sums: workspace too small");
+    const long long tot = (long long)B * n;
+    const int nblk = (int)std::min<long long>(512, ceil_div64(tot, 2048));
+    const double inv = 1.0 / ((double)P * (double)B_norm * (double)n);
+    const size_t es = dtype == DADMM_F64 ? 8 : 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PROF_LOSS, s);
+    double* part = (double*)ws;
+    if (dtype == DADMM_F32) {
+        loss_sums_partial_kernel<float><<<dim3(nblk, k1 - k0), 256, 0, s>>>((const float*)agent_sum + (size_t)k0 * tot, (const float*)label, tot, part);
+        DADMM_LAUNCHED();
+        loss_sums_final_kernel<float><<<k1 - k0, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (float*)((char*)losses + (size_t)k0 * es));
+        DADMM_LAUNCHED();
+    } else if (dtype == DADMM_F64) {
+        loss_sums_partial_kernel<double><<<dim3(nblk, k1 - k0), 256, 0, s>>>((const double*)agent_sum + (size_t)k0 * tot, (const double*)label, tot, part);
+        DADMM_LAUNCHED();
+        loss_sums_final_kernel<double><<<k1 - k0, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (double*)((char*)losses + (size_t)k0 * es));
+        DADMM_LAUNCHED();
+    } else {
+        DADMM_FAIL(-1, "loss_from_sums: unknown dtype %d", dtype);
     }
     return 0;
 }

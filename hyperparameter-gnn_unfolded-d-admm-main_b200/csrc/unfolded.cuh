@@ -121,6 +121,8 @@ struct LevelFwdParams {
     T *y_next, *U_out, *graw;
     int32_t* flags;
     SplitOut sp;                        // fp16 split of y_{k+1} (fp32 only)
+    T* agent_sum;                       // optional [B][n]: sum over agents of y_{k+1} (lean form, TB == 1)
+    double* sq_part;                    // optional [gridDim.x]: per-CTA sum of y_{k+1}^2
 };
 
 template <typename T>
@@ -317,10 +319,13 @@ level_fwd_kernel(const LevelFwdParams<T> p) {
     if (first) __syncthreads();                          // (the tile-load barrier below covers the other levels)
     T nonfinite = (T)0;
     const T nG = -p.G, nV = -p.V;
+    const bool sums = LEAN && p.agent_sum != nullptr;
+    float sq_tot = 0.f;
 
     for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
     const int i = chunk * CH + lane * VEC;
     const bool act_i = LEAN || i < p.n;
+    V vsum = vzero<T, VEC>();
     if (!first) {
         if (chunk != chunk_begin) __syncthreads();      // rows of the previous chunk are still being read
         for (int bl = 0; bl < p.TB; ++bl) {
@@ -417,11 +422,48 @@ level_fwd_kernel(const LevelFwdParams<T> p) {
                     if (do_split) store_split<VEC>(p.sp, off, yn, sc, 1.f);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) amax_f = fmaxf(amax_f, fabsf(yn.v[v]));
+                    if constexpr (LEAN) {
+                        if (sums) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                vsum.v[v] += yn.v[v];
+                                sq_tot = fmaf((float)yn.v[v], (float)yn.v[v], sq_tot);
+                            }
+                        }
+                    }
                 }
             }
         }
     }
+    if constexpr (LEAN && sizeof(T) == 4) {
+        if (sums) {      // TB == 1: sum of the tile's rows over the warps -> agent_sum[b0][chunk]
+            __syncthreads();                                     // every warp is done with the y_k tile
+            float* red = reinterpret_cast<float*>(S0);
+            *reinterpret_cast<V*>(red + warp * CH + lane * VEC) = vsum;
+            __syncthreads();
+            if (threadIdx.x < CH) {
+                float a = 0.f;
+                for (int wq = 0; wq < nwarps; ++wq) a += red[wq * CH + threadIdx.x];
+                p.agent_sum[(unsigned)b0 * p.n + chunk * CH + threadIdx.x] = a;
+            }
+        }
+    }
     }   // chunk loop
+    if constexpr (LEAN && sizeof(T) == 4) {
+        if (sums) {
+            float w = sq_tot;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            __syncthreads();
+            if (lane == 0) sAlpha[warp] = w;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0;
+                for (int wq = 0; wq < nwarps; ++wq) t += (double)sAlpha[wq];
+                p.sq_part[blockIdx.x] = t;
+            }
+        }
+    }
     if constexpr (sizeof(T) == 4) {
         amax_bits = __float_as_uint(amax_f);
         if (p.sp.amax_out) publish_amax(amax_bits, p.sp.amax_out, sAmax);
@@ -761,6 +803,66 @@ __global__ void __launch_bounds__(256) reduce_level_kernel(const T* __restrict__
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
         if (threadIdx.x < 3) row_k[pp * 4 + threadIdx.x] = (T)s;
         else if (row_prev) row_prev[pp * 4 + 3] = (T)s;
+    }
+}
+
+// sumsq[k] = sum of the per-CTA partials the forward level k left in part[k][0..grid), for k = k_first + blockIdx.x
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restrict__ part, size_t row_stride, int grid, int k_first,
+                                                          double* __restrict__ sumsq) {
+    const int k = k_first + blockIdx.x;
+    double a = 0;
+    for (int i = threadIdx.x; i < grid; i += blockDim.x) a += part[(size_t)k * row_stride + i];
+    __shared__ double sh[8];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        sumsq[k] = t;
+    }
+}
+
+// partial[k][blk] = (sum S[k] * label, sum label^2) over the block's share of [B*n]
+template <typename T>
+__global__ void __launch_bounds__(256) loss_sums_partial_kernel(const T* __restrict__ S, const T* __restrict__ label, long long tot,
+                                                                double* __restrict__ part) {
+    const T* Sk = S + (size_t)blockIdx.y * tot;
+    double d = 0, l2 = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const double l = (double)label[i];
+        d += (double)Sk[i] * l;
+        l2 += l * l;
+    }
+    __shared__ double sh[2][8];
+    d = warp_sum(d);
+    l2 = warp_sum(l2);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = d; sh[1][threadIdx.x >> 5] = l2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = t;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) loss_sums_final_kernel(const double* __restrict__ part, int nblk, const double* __restrict__ sumsq,
+                                                              int P, double inv, T* __restrict__ losses) {
+    const int k = blockIdx.x;
+    double d = 0, l2 = 0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+        d += part[((size_t)k * nblk + i) * 2];
+        l2 += part[((size_t)k * nblk + i) * 2 + 1];
+    }
+    __shared__ double sh[2][8];
+    d = warp_sum(d);
+    l2 = warp_sum(l2);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = d; sh[1][threadIdx.x >> 5] = l2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double td = 0, tl = 0;
+        for (int w = 0; w < 8; ++w) { td += sh[0][w]; tl += sh[1][w]; }
+        losses[k] = (T)((sumsq[k] - 2.0 * td + (double)P * tl) * inv);
     }
 }
 

@@ -14,7 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
@@ -42,6 +42,11 @@ class Factor(C.Structure):
     _fields_ = [("m", C.c_int32), ("F1", C.c_void_p), ("F2", C.c_void_p), ("rhs", C.c_void_p)]
 
 
+class LossSums(C.Structure):
+    """Label-free per-iteration sums written by ``dadmm_unfolded_fwd`` (``dadmm_loss_sums``)."""
+    _fields_ = [("agent_sum", C.c_void_p), ("sumsq", C.c_void_p), ("valid", C.POINTER(C.c_int32))]
+
+
 class DadmmError(RuntimeError):
     pass
 
@@ -53,7 +58,7 @@ def _load():
             "There is no CPU fallback for the D-ADMM hot path.")
     lib = C.CDLL(LIB_PATH)
     i32, i64, vp, dbl, sz = C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_size_t
-    GP, CP, HP, FP = C.POINTER(Graph), C.POINTER(Clamps), C.POINTER(Hyp), C.POINTER(Factor)
+    GP, CP, HP, FP, SP = C.POINTER(Graph), C.POINTER(Clamps), C.POINTER(Hyp), C.POINTER(Factor), C.POINTER(LossSums)
     sigs = {
         "dadmm_abi_version": (i32, []),
         "dadmm_last_error": (C.c_char_p, []),
@@ -71,7 +76,7 @@ def _load():
         "dadmm_partials_elems": (sz, [i32, i32, i32, i32]),
         "dadmm_reduce_hyp": (i32, [i32, i32, i32, i32, vp, i32, vp, i64, i64, i64, i32, vp]),
         "dadmm_unfolded_fwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp, sz,
-                                     vp, vp]),
+                                     vp, SP, vp]),
         "dadmm_unfolded_bwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp,
                                      C.POINTER(dbl), vp, vp, sz, vp]),
         "dadmm_unfolded_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32, i32, i32]),
@@ -79,6 +84,7 @@ def _load():
         "dadmm_loss_fwd": (i32, [i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, sz, vp]),
         "dadmm_loss_bwd": (i32, [i32, i32, i32, i32, i32, vp, vp, C.POINTER(dbl), vp, vp]),
         "dadmm_loss_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
+        "dadmm_loss_from_sums": (i32, [i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -229,13 +229,23 @@ class Unfolded(torch.autograd.Function):
         R_save = torch.empty((K, B, P, n), dtype=y0.dtype, device=dev) if need_grad else None
         carr = _clamps_array(clamps)
         fac, fac_t = _factor_struct(factor, P, n, y0), _factor_struct(factor_t, P, n, y0)
+        sums = None
+        if handle is not None and K >= 3 and y0.dtype == torch.float32:
+            # label-free loss sums (dadmm_loss_sums): lets compute_loss skip its full read of Y for the iterations the
+            # library reports as valid
+            S = torch.empty((K, B, n), dtype=y0.dtype, device=dev)
+            sq = torch.empty(K, dtype=torch.float64, device=dev)
+            valid = (C.c_int32 * K)()
+            sums = (_lib.LossSums(ptr(S), ptr(sq), valid), S, sq, valid)
         with device_guard(dev):
             wsb = lib.dadmm_unfolded_ws_bytes(dt, al, B, P, n, K, 0, fac[0].m if fac else 0)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             check(lib.dadmm_unfolded_fwd(dt, al, B, P, n, K, C.byref(graph.c), carr, ptr(hyp), ptr(W),
                                          C.byref(fac[0]) if fac else None, ptr(Atb), ptr(y0),
                                          ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(ws), wsb, ptr(flags),
-                                         stream_ptr(dev)), "dadmm_unfolded_fwd")
+                                         C.byref(sums[0]) if sums else None, stream_ptr(dev)), "dadmm_unfolded_fwd")
+        if sums is not None and any(sums[3]):
+            handle.sums = (sums[1], sums[2], [bool(v) for v in sums[3]], Y.data_ptr())
         if need_grad:
             ctx.save_for_backward(hyp, Wt, y0, U0, d0, Y, U_save, R_save)
             ctx.graph, ctx.clamps, ctx.algo = graph, carr, al
@@ -270,18 +280,46 @@ class Unfolded(torch.autograd.Function):
         return (ghyp,) + (None,) * 13
 
 
-def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[int] = None) -> torch.Tensor:
-    """losses[k] = sum (Y[k]-label)^2 / (P*B_norm*n)  (gnn_dlasso_utils.py:54-66).  No autograd."""
+def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[int] = None, handle=None) -> torch.Tensor:
+    """losses[k] = sum (Y[k]-label)^2 / (P*B_norm*n)  (gnn_dlasso_utils.py:54-66).  No autograd.
+
+    When ``handle`` carries the label-free sums the forward pass left behind (``dadmm_loss_sums``), the inner iterations
+    are evaluated from them -- a read of [K,B,n] instead of [K,B,P,n] -- and only the first and the last iteration (the
+    one the drivers back-propagate) read Y."""
     dev = require_cuda(Y, label)
     K, B, P, n = Y.shape[:4]
     Yc, lab = Y.contiguous(), label.contiguous()
     dt = dtype_code(Yc)
+    Bn = int(B_norm or B)
     losses = torch.empty(K, dtype=Y.dtype, device=dev)
+    sums = getattr(handle, "sums", None)
+    if sums is not None and (sums[3] != Yc.data_ptr() or len(sums[2]) != K):
+        sums = None
     with device_guard(dev):
         wsb = lib.dadmm_loss_ws_bytes(dt, K, B, P, n)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        check(lib.dadmm_loss_fwd(dt, K, B, P, n, int(B_norm or B), ptr(Yc), ptr(lab), ptr(losses), ptr(ws), wsb,
-                                 stream_ptr(dev)), "dadmm_loss_fwd")
+
+        def exact(k0, k1):
+            es = Yc.element_size()
+            check(lib.dadmm_loss_fwd(dt, k1 - k0, B, P, n, Bn, C.c_void_p(Yc.data_ptr() + k0 * B * P * n * es), ptr(lab),
+                                     C.c_void_p(losses.data_ptr() + k0 * es), ptr(ws), wsb, stream_ptr(dev)), "dadmm_loss_fwd")
+        if sums is None:
+            exact(0, K)
+        else:
+            S, sq, valid, _ = sums
+            use = list(valid)
+            use[K - 1] = False                 # the final iteration is always evaluated exactly from Y
+            k = 0
+            while k < K:                       # maximal runs of equal kind
+                j = k
+                while j < K and use[j] == use[k]:
+                    j += 1
+                if use[k]:
+                    check(lib.dadmm_loss_from_sums(dt, k, j, B, P, n, Bn, ptr(S), ptr(sq), ptr(lab), ptr(losses), ptr(ws), wsb,
+                                                   stream_ptr(dev)), "dadmm_loss_from_sums")
+                else:
+                    exact(k, j)
+                k = j
     return losses
 
 
@@ -290,6 +328,7 @@ class FusedLossHandle:
 
     def __init__(self):
         self.pending = None
+        self.sums = None          # (agent_sum [K,B,n], sumsq [K], valid [K], Y.data_ptr()) left by Unfolded.forward
 
     def offer(self, label, coefs, sentinel) -> bool:
         if self.pending is not None:
@@ -314,7 +353,7 @@ class MSELoss(torch.autograd.Function):
     def forward(ctx, Y, label, B_norm, handle):
         ctx.save_for_backward(Y, label)
         ctx.B_norm, ctx.handle = B_norm, handle
-        return loss_per_iteration(Y, label, B_norm)
+        return loss_per_iteration(Y, label, B_norm, handle)
 
     @staticmethod
     def backward(ctx, g_losses):

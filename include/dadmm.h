@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 3
+#define DADMM_ABI_VERSION 4
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -108,6 +108,18 @@ typedef struct dadmm_factor {
     const void* rhs;
 } dadmm_factor;
 
+/* Optional side outputs of dadmm_unfolded_fwd for the per-iteration loss (gnn_dlasso_utils.py:54-66), so that
+ * compute_loss need not read Y[K,B,P,n] again.  The label is not known to forward(), hence label-free sums:
+ *   agent_sum[k][b][i] = sum_p Y[k][b][p][i]        sumsq[k] = sum_{b,p,i} Y[k][b][p][i]^2
+ * and losses[k] = (sumsq[k] - 2 <agent_sum[k], label> + P sum label^2) / (P*B_norm*n)   (dadmm_loss_from_sums).
+ * valid[k] (host, written during the call) tells for which iterations the sums were produced: the fused tensor-core
+ * path on full tiles, k >= 1; the others must be evaluated from Y with dadmm_loss_fwd. */
+typedef struct dadmm_loss_sums {
+    void* agent_sum;  /* device [K,B,n], dtype of the state */
+    double* sumsq;    /* device [K] */
+    int32_t* valid;   /* host   [K] */
+} dadmm_loss_sums;
+
 int dadmm_abi_version(void);
 const char* dadmm_last_error(void);
 /* 0 when the current CUDA device is an sm_100 part this library was built for */
@@ -179,7 +191,7 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
                        const void* Atb,
                        const void* y0, const void* U0, const void* d0,
                        void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
-                       int32_t* flags, dadmm_stream_t stream);
+                       int32_t* flags, const dadmm_loss_sums* sums /* may be NULL */, dadmm_stream_t stream);
 /* Reverse sweep: gY [K,B,P,n] dense upstream gradient (may be NULL) and/or the fused loss term
  * loss_coef[k]*(Y[k]-label) (label [B,n], loss_coef host [K], both may be NULL).  Wt = AtA^T [P,n,n];
  * factor_t (may be NULL) factorises Wt (for the symmetric AtA: the forward's factor).  Writes ghyp [K,P,4]. */
@@ -202,6 +214,10 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
 int dadmm_loss_bwd(int dtype, int K, int B, int P, int n, const void* Y, const void* label,
                    const double* coef, void* gY, dadmm_stream_t stream);
 size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n);
+/* losses[k], k0 <= k < k1, from the side outputs of dadmm_unfolded_fwd (see dadmm_loss_sums); same workspace size. */
+int dadmm_loss_from_sums(int dtype, int k0, int k1, int B, int P, int n, int64_t B_norm, const void* agent_sum,
+                         const double* sumsq, const void* label, void* losses, void* ws, size_t ws_bytes,
+                         dadmm_stream_t stream);
 
 #ifdef __cplusplus
 }

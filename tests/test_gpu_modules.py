@@ -260,3 +260,35 @@ def test_bench_workload_shapes_k_step_gate_through_the_modules():
         print(f"cfg4 shapes, {tag}: trimmed Y[k] vs fp64 " + " ".join(f"{_trimmed_rel_l2(Y[k], Y64[k]):.1e}" for k in range(w["K"]))
               + " (exact-FMA " + " ".join(f"{_trimmed_rel_l2(Ys[k], Y64[k]):.1e}" for k in range(w["K"])) + f"); dparam {rel_l2(gp, g64):.2e} "
               f"(exact-FMA {rel_l2(gs, g64):.2e}); loss {lf:.7f} vs {l64:.7f}")
+
+
+def test_losses_from_forward_side_sums_match_the_full_read_of_Y():
+    """the fused forward leaves label-free sums (sum over agents of Y[k], sum of Y[k]^2) behind, and
+    compute_loss evaluates the inner iterations from them instead of reading Y[K,B,P,n] again.  Same losses as the
+    direct kernel to 2e-6 relative (the direct kernel is the one the golden fixtures pin), first / last iteration exact."""
+    import unfolded_DLASSO
+    import gnn_dlasso_utils
+    from dadmm_b200 import functional as DF
+    P, n, m, K, B = 16, 256, 64, 6, 128          # P >= 16: one problem per CTA tile, the configuration that emits the sums
+    pr = random_problem(P, n, m, B, K, seed=5, a_scale=0.1)
+    args = argparse.Namespace(m=m, n=n, P=P, GHN_iter_num=K, DADMM_mode="diff", alpha_max=0.1, tau_max=0.99, rho_max=0.99,
+                              eta_max=0.99, max_penalty_threshold=0.8, penalty_reduction_factor=0.95, batch_size=B, snr=4)
+    model = unfolded_DLASSO.DLASSO_unfolded(pr["A"].to(DEV), args).to(DEV)
+    with torch.no_grad():
+        model.seq_hyp.param.copy_(pr["param"].to(DEV))
+    label = pr["label"].to(DEV)
+    Y, _ = model(pr["b"].to(DEV), pr["graphs"])
+    h = Y._dadmm_handle
+    assert h.sums is not None and h.sums[2] == [False] + [True] * (K - 1)
+    # the side outputs themselves
+    assert rel_l2(h.sums[0].cpu(), Y.detach()[..., 0].sum(dim=2)[:].cpu() * torch.tensor(h.sums[2]).view(K, 1, 1)) < 1e-6
+    sq = (Y.detach().double() ** 2).sum(dim=(1, 2, 3, 4))
+    assert torch.allclose(h.sums[1][1:].cpu(), sq[1:].cpu(), rtol=1e-6)
+    direct = DF.loss_per_iteration(Y.detach(), label)                # no handle: full read of Y
+    fused = DF.loss_per_iteration(Y.detach(), label, None, h)
+    assert torch.equal(direct[0], fused[0]) and torch.equal(direct[-1], fused[-1])
+    assert float(((direct - fused).abs() / direct.abs()).max()) < 2e-6
+    lm, lf = gnn_dlasso_utils.compute_loss(Y, label)                  # the drop-in entry point takes the fused route
+    assert math.isclose(float(lm), float(direct.mean()) + 1e-8, rel_tol=2e-6) and math.isclose(float(lf), float(direct[-1]) + 1e-8, rel_tol=1e-7)
+    lf.backward()
+    assert model.seq_hyp.param.grad is not None and bool(torch.isfinite(model.seq_hyp.param.grad).all())
