@@ -10,10 +10,13 @@
 // rounding of the accumulation dominates.  Three MMAs per k-step (lo*hi, hi*lo, hi*hi) at the f16 rate cost
 // half of the 3xTF32 scheme, and because the operands arrive in global memory already split
 // (split_f16_kernel; W once per operator, x by its producer), the GEMM kernel has no conversion stage:
-// TMA -> shared memory -> tcgen05.mma, 80 KB of shared-memory traffic per 768 MMA cycles instead of 144 KB.
+// TMA -> shared memory -> tcgen05.mma.
 //
-// Accumulation is chunked exactly as in contract_tc.cuh (64 k per tensor-core partial sum, fp32 RN adds in
-// registers) because the TMEM accumulator truncates.  CTA pairs (cta_group::2), 256 x 256 output tile per pair.
+// Accumulation is chunked (64 or 128 k per tensor-core partial sum, fp32 RN adds in registers; see KB_PER_CHUNK)
+// because the TMEM accumulator truncates.  CTA pairs (cta_group::2), 256 operator rows x NT batch columns per pair
+// (NT = 256, or 128 for small batches: Geo<NT>).  The same kernel serves the single-stage contraction AtA y and both
+// stages of the two-stage form A^T (A y - b): the first stage writes its result straight as the next stage's fp16
+// split (Params::t_hi), optionally seeded with -b; the second (or only) stage writes fp32, optionally `+=` or `- sub`.
 #pragma once
 #include <cuda_fp16.h>
 

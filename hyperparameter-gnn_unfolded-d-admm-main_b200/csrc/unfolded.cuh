@@ -20,12 +20,16 @@
 //     -- here 2L x is evaluated as 2(deg x_q - sum_j x_j) over the plain neighbour list (half the terms of the
 //        event order; the backward pass has no bit pattern to reproduce).
 //
-// These kernels are instruction-issue sensitive (ncu, round 1: the first version executed ~1100 warp
-// instructions per row segment and sat at 22 % of HBM peak), so: the tile's neighbour lists are staged in shared
-// memory once per CTA as pre-scaled row offsets (no shuffles / index arithmetic in the inner loop), rows are
-// walked without integer division, the next row's global loads are issued before the current row's
-// shared-memory work (register double buffering), and the four hyper-parameter partial sums share one
-// 6-shuffle reduction.
+// (In the fused fp16 path a_k already holds AtA y_k - Atb -- the contraction's epilogue, or its first stage
+// A^T(A y_k - b), subtracts the observation term -- and the saved stream is that residual; the backward level
+// rebuilds r_k from it.)
+//
+// These kernels are instruction-issue and latency sensitive (ncu, round 1: the first version executed ~1100 warp
+// instructions per row segment and sat at 22 % of HBM peak), so: the tile's neighbour lists and per-agent scalars are
+// staged in shared memory once per CTA, rows are walked without integer division, the y_k tile arrives by cp.async,
+// the four hyper-parameter partial sums share one 6-shuffle reduction, and the fused path's configuration on full
+// tiles runs LEAN template instantiations without guards, zero-fills or select chains (see level_fwd_kernel /
+// level_bwd_kernel).  Register double-buffering of the next row was measured twice and lost to occupancy both times.
 #pragma once
 #include <cuda_fp16.h>
 
