@@ -226,6 +226,8 @@ def run_ours(opt, w):
     model = unfolded_DLASSO.DLASSO_unfolded(A_dev, args).to(dev)
     model.contract_algo = opt.algo
     model.two_stage = not opt.one_stage
+    if opt.no_pdl:
+        _lib.set_pdl(False)               # A/B switch: classic stream-ordered launches for the K-loop chain
     two_stage = bool(model.two_stage and _lib.lib.dadmm_unfolded_uses_factor(0, _lib.ALGOS[opt.algo], B_loc, w["P"], w["n"], w["m"]))
     with torch.no_grad():
         model.seq_hyp.param.copy_(param)
@@ -339,13 +341,15 @@ def run_ours(opt, w):
                        "batch_per_gpu": B_loc, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "contraction": opt.algo + (" two-stage A^T(A y)" if two_stage else " AtA y"), "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
                        if B_loc * w["P"] * w["n"] * 4 > 126e6 else "working set fits L2 (small config)",
-                       "step": "forward K iters + compute_loss + loss_final.backward + grad allreduce + Adam"},
+                       "step": "forward K iters + compute_loss + loss_final.backward + grad allreduce + Adam",
+                       "launch_chain": "classic" if opt.no_pdl else "programmatic dependent launch",
+                       "operator_split": "cached with the operator (a constructor-time constant, like the reference's AtA)"},
             "clocks": clocks,
             "e2e": {"value": w["K"] * B_glob / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e,
                     "h2d_bytes_per_step": (b_host.numel() + label_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "loss_final": loss_val,
             "roofline": roofline, "kernel_breakdown_ms": breakdown}
-    if opt.cpu_baseline:
+    if opt.cpu_baseline and world == 1:       # rank 0 at N=1 only
         run, B_ref = cpu_baseline_sample(w)
         t = min(run() for _ in range(1 if w["P"] >= 50 else 2))
         line["cpu_baseline"] = {"value": w["K"] * B_ref / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -449,6 +453,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--batch", type=int, default=None,
                     help="diagnostic: override the workload's global batch (the reported config then names it)")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B switch: launch the K-loop chain without programmatic dependent launch")
     ap.add_argument("--one-stage", action="store_true",
                     help="keep the contraction on the explicit AtA operator (A/B switch for the two-stage form A^T (A y))")
     opt = ap.parse_args()

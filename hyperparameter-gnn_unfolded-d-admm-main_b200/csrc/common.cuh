@@ -5,6 +5,9 @@
 #include <math.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
 
 namespace dadmm {
 
@@ -125,6 +128,45 @@ __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The K-loop is a chain of ~1000 short dependent kernels per training step; with the
+// attribute below the next kernel of the chain is scheduled while the current one drains, so its launch latency and
+// its constant-input prologue (barrier / TMEM set-up, neighbour lists, per-agent scalars) overlap the predecessor's
+// tail.  Rules every chain kernel follows: (1) `pdl_wait()` before the first access to anything an earlier kernel of
+// the chain writes or still reads, executed by every thread; (2) `pdl_trigger()` only AFTER its own wait -- so when a
+// kernel starts, everything older than its immediate predecessor is complete and visible, and only call-constant
+// inputs (graph lists, the hyper-parameter table) may be touched before the wait.  Both instructions are no-ops in a
+// kernel launched the classic way.  DADMM_PDL=0 / dadmm_set_pdl(0) turn the attribute off (A/B measurements, tests).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern std::atomic<int> g_pdl;           // -1: not read yet; dadmm_set_pdl() flips it at run time
+inline bool pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DADMM_PDL");
+        v = (e && !strcmp(e, "0")) ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

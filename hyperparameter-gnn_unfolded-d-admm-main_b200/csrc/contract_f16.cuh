@@ -68,6 +68,8 @@ constexpr int KB_PER_CHUNK = DADMM_F16_KB_PER_CHUNK;
 // ---------------------------------------------------------------------------------------------------
 // max |x| over a tensor as raw float bits (non-negative floats order like unsigned ints)
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     unsigned m = 0;
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
                                                         int n_pad, const unsigned* __restrict__ amax_bits,
                                                         __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ exp_out,
                                                         unsigned* __restrict__ l1_out) {
+    pdl_wait();
+    pdl_trigger();
     const int e = scale_exponent(*amax_bits);
     // 2^e can exceed the float range for tiny tensors; apply it in two factors
     const float s1 = pow2f(e / 2), s2 = pow2f(e - e / 2);
@@ -217,6 +221,10 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
     tcgen05_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // barrier / TMEM set-up above touched no global memory: it overlaps the tail of the preceding kernel (common.cuh)
+    pdl_wait();
+    pdl_trigger();
 
     const int tiles_per_agent = p.m_tiles * p.n_tiles;
     const int n_chunks = (p.k_blocks + p.kbc - 1) / p.kbc;
@@ -478,13 +486,14 @@ inline int split_tensor(const float* x, long long rows, int n, long long ld, voi
     if (ld == n) {
         const long long tot = rows * n;
         const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(tot, 1024));
-        amax_kernel<<<nblk, 256, 0, s>>>(x, tot, v.amax);
+        DADMM_CUDA(launch_chain(amax_kernel, dim3(nblk), dim3(256), 0, s, x, tot, v.amax));
     } else {
         for (long long r = 0; r < rows; ++r) amax_kernel<<<1, 256, 0, s>>>(x + r * ld, n, v.amax);   // strided rows: rare
     }
     DADMM_LAUNCHED();
     const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
-    split_f16_kernel<<<nblk, 256, 0, s>>>(x, rows, n, ld, pad8(n), v.amax, v.hi, v.lo, v.exp, want_l1 ? v.l1 : nullptr);
+    DADMM_CUDA(launch_chain(split_f16_kernel, dim3(nblk), dim3(256), 0, s, x, rows, n, ld, pad8(n), (const unsigned*)v.amax, v.hi, v.lo,
+                            v.exp, want_l1 ? v.l1 : (unsigned*)nullptr));
     DADMM_LAUNCHED();
     return 0;
 }
@@ -509,7 +518,7 @@ inline int amax_tensor(const float* x, long long tot, unsigned* out, cudaStream_
     DADMM_CUDA(cudaMemsetAsync(out, 0, 4, s));
     ProfScope prof(PROF_SPLIT, s);
     const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(tot, 1024));
-    amax_kernel<<<nblk, 256, 0, s>>>(x, tot, out);
+    DADMM_CUDA(launch_chain(amax_kernel, dim3(nblk), dim3(256), 0, s, x, tot, out));
     DADMM_LAUNCHED();
     return 0;
 }
@@ -560,7 +569,7 @@ inline int launch_nt(Params& p, const Split& x, int n_in, int B, int P, tc::Enco
     }
     const int clusters = std::min(num_sms / 2, p.total_tiles);
     ProfScope prof(stage1 ? PROF_CONTRACT_STAGE1 : PROF_CONTRACT_TC, s);
-    contract_f16_kernel<NT><<<2 * clusters, THREADS, G::SMEM, s>>>(mwh, mwl, mxh, mxl, p);
+    DADMM_CUDA(launch_chain(contract_f16_kernel<NT>, dim3(2 * clusters), dim3(THREADS), (size_t)G::SMEM, s, mwh, mwl, mxh, mxl, p));
     DADMM_LAUNCHED();
     return 0;
 }

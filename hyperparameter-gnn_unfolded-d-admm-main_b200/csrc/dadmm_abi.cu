@@ -18,6 +18,7 @@
 namespace dadmm {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_pdl{-1};
 
 // ------------------------------------------------------------------------------------------
 // per-kind kernel timing
@@ -340,7 +341,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
 #define DADMM_LAUNCH_LFWD(VEC, LEAN, NTHR)                                                      \
     {                                                                                           \
         if (int e = allow_smem(level_fwd_kernel<T, VEC, LEAN, NTHR>, smem)) return e;           \
-        level_fwd_kernel<T, VEC, LEAN, NTHR><<<c.grid, NTHR, smem, s>>>(p);                     \
+        DADMM_CUDA(launch_chain(level_fwd_kernel<T, VEC, LEAN, NTHR>, dim3(c.grid), dim3(NTHR), smem, s, p)); \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
@@ -372,7 +373,7 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, int top, const void* y,
                           const void* U_prev, const void* d0, const void* graw, void* Tb, void* C, void* ga,
                           const void* gY_prev, const void* label, double coef_prev, void* partials, const SplitOut& sp,
-                          int graw_is_residual, cudaStream_t s) {
+                          int graw_is_residual, cudaStream_t s, const double* coef_dev = nullptr) {
     LevelBwdParams<T> p;
     p.sp = sp;
     p.graw_is_residual = graw_is_residual;
@@ -386,8 +387,9 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.y = (const T*)y; p.U_prev = (const T*)U_prev; p.d0 = (const T*)d0; p.graw = (const T*)graw;
     p.Tb = (T*)Tb; p.C = (T*)C; p.ga = (T*)ga;
     p.gY_prev = (const T*)gY_prev;
-    p.label = (coef_prev != 0.0) ? (const T*)label : nullptr;
+    p.label = (coef_prev != 0.0 || coef_dev) ? (const T*)label : nullptr;
     p.coef_prev = (T)coef_prev;
+    p.coef_dev = p.label ? coef_dev : nullptr;
     p.partials = (T*)partials;
     StepCfg c;
     size_t smem = 0;
@@ -400,7 +402,7 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
 #define DADMM_LAUNCH_LBWD(VEC, LEAN, NTHR)                                                      \
     {                                                                                           \
         if (int e = allow_smem(level_bwd_kernel<T, VEC, LEAN, NTHR>, smem)) return e;           \
-        level_bwd_kernel<T, VEC, LEAN, NTHR><<<c.grid, NTHR, smem, s>>>(p);                     \
+        DADMM_CUDA(launch_chain(level_bwd_kernel<T, VEC, LEAN, NTHR>, dim3(c.grid), dim3(NTHR), smem, s, p)); \
     }
     bool launched = false;
     if constexpr (sizeof(T) == 4) {
@@ -420,6 +422,18 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
 #undef DADMM_LAUNCH_LBWD
     DADMM_LAUNCHED();
     return 0;
+}
+
+// partial-sum rows of the reverse sweep: K levels x [csplit][B][P][4] (the chunking level_bwd_impl picks), reduced by one
+// launch after the sweep
+static size_t sweep_part_elems(int dtype, int B, int P, int n, int K, size_t* level_stride = nullptr, int* nchunks = nullptr) {
+    StepCfg c;
+    if (step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return 0;
+    const int cs = level_bwd_csplit(B, c.TB, c.nchunks);
+    const size_t stride = (size_t)cs * B * P * 4;
+    if (level_stride) *level_stride = stride;
+    if (nchunks) *nchunks = cs;
+    return stride * (size_t)std::max(K, 1);
 }
 
 static size_t amax_slots_bytes(int K) { return ((size_t)(K + 1) * 4 + 255) / 256 * 256; }
@@ -478,9 +492,9 @@ static size_t unfolded_cw(int dtype, int algo, int B, int P, int n, int m) {
 
 // one contraction of the fused path from prepared operands: out (+)= W x (- sub); with `rhs` (two-stage only) the
 // subtracted term enters the first stage instead: out = F2 (F1 x - rhs)
-static int fused_contract(const FusedWs& f, char* w8, int B, int P, int n, int m, float* out, int accumulate, cudaStream_t s,
+// (w8 = operator split(s): head of the workspace, or the caller's persistent dadmm_op_split buffer; xsp = split of x)
+static int fused_contract(const FusedWs& f, char* w8, char* xsp, int B, int P, int n, int m, float* out, int accumulate, cudaStream_t s,
                           unsigned* amax_out, const float* sub, int fast, const float* rhs = nullptr) {
-    char* xsp = w8 + f.w1 + f.w2;
     if (!f.two) return f16::launch(B, P, n, n, w8, xsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast);
     char* tsp = xsp + f.xb;
     const unsigned* rhs_amax = (const unsigned*)(tsp + 48);       // spare scalar slot of the t split header
@@ -497,12 +511,20 @@ static int fused_prepare(const FusedWs& f, char* w8, int P, int n, int m, const 
     return f16::split_tensor((const float*)fac->F2, (long long)P * n, m, m, w8 + f.w1, s);
 }
 
+static int check_op_split(const dadmm_op_split* ops, int dtype, int algo, int B, int P, int n, int m) {
+    if (!ops || !ops->buf) return 0;
+    const FusedWs f = fused_ws(dtype, algo, B, P, n, m);
+    if (ops->bytes < f.w1 + f.w2) DADMM_FAIL(-1, "op_split: buffer of %zu bytes, %zu needed", ops->bytes, f.w1 + f.w2);
+    if (!aligned_to(ops->buf, 256)) DADMM_FAIL(-5, "op_split: buffer must be 256-byte aligned");
+    return 0;
+}
+
 template <typename T>
 static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
                              const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* fac,
                              const void* Atb, const void* y0,
                              const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, int32_t* flags,
-                             const dadmm_loss_sums* sums, cudaStream_t s) {
+                             const dadmm_loss_sums* sums, const dadmm_op_split* ops, cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
     if (N >= (1ull << 31)) DADMM_FAIL(-1, "unfolded: B*P*n must stay below 2^31 per device (shard the batch)");
@@ -524,10 +546,12 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     const bool fused = fused_f16(dtype, algo, B, P, n);
     const size_t wb = fw.w1 + fw.w2;
     f16::Split xs{};
+    char* wsp = (fused && ops && ops->buf) ? (char*)ops->buf : w8;       // operator split: persistent buffer or workspace head
     if (fused) {
         xs = f16::split_view(w8 + wb, (long long)B * P, n);
         DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
-        if (int e = fused_prepare(fw, w8, P, n, mf, W, fac, s)) return e;
+        if (!(ops && ops->buf && ops->ready))
+            if (int e = fused_prepare(fw, wsp, P, n, mf, W, fac, s)) return e;
         if (int e = f16::split_tensor((const float*)y0, (long long)B * P, n, n, w8 + wb, s)) return e;
         if (fw.two && fac->rhs)
             if (int e = f16::amax_tensor((const float*)fac->rhs, (long long)B * P * mf, (unsigned*)(w8 + wb + fw.xb + 48), s)) return e;
@@ -544,7 +568,7 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
         // stream (R_save[k]) -- the forward level neither reads Atb nor writes r_k; the backward rebuilds r_k from a_k'
         char* ak = (fused && R_save) ? (char*)R_save + (size_t)k * NB : a;
         if (fused) {
-            if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)ak, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1, rhs))
+            if (int e = fused_contract(fw, wsp, w8 + wb, B, P, n, mf, (float*)ak, 0, s, nullptr, (const float*)Atb, algo == DADMM_ALGO_TC_F16X1, rhs))
                 return e;
             if (k < K - 1) sp = SplitOut{xs.hi, xs.lo, xs.exp, k ? slots + k : nullptr, slots + k + 1};
         } else {
@@ -567,7 +591,8 @@ static int unfolded_fwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     if (sums && sums_first < K) {
         DADMM_CUDA(cudaMemsetAsync(sums->sumsq, 0, (size_t)K * sizeof(double), s));
         ProfScope prof(PROF_LOSS, s);
-        sumsq_final_kernel<<<K - sums_first, 256, 0, s>>>(sq_part, sq_row, sums_grid, sums_first, sums->sumsq);
+        DADMM_CUDA(launch_chain(sumsq_final_kernel, dim3(K - sums_first), dim3(256), 0, s, (const double*)sq_part, sq_row, sums_grid,
+                                sums_first, sums->sumsq));
         DADMM_LAUNCHED();
     }
     return 0;
@@ -578,7 +603,8 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                              const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* fac,
                              const void* y0, const void* U0,
                              const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
-                             const void* label, const double* loss_coef, void* ghyp, void* ws, cudaStream_t s) {
+                             const void* label, const double* loss_coef, const double* loss_coef_dev, void* ghyp, void* ws,
+                             const dadmm_op_split* ops, cudaStream_t s) {
     const size_t es = sizeof(T);
     const size_t N = (size_t)B * P * n, NB = N * es;
     const int mf = fac ? fac->m : 0;
@@ -587,36 +613,38 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
     const size_t NBa = (NB + 255) / 256 * 256;      // 256-byte aligned workspace regions
     char* w8 = (char*)ws;
     char *Tb = w8 + cw, *C = Tb + NBa, *ga = C + NBa, *part = ga + NBa;
-    unsigned* slots = (unsigned*)(part + (partials_elems(B, P, n) * es + 255) / 256 * 256);   // max|adj(y_{k+1})| bits
+    size_t part_stride = 0;              // elements between the partial rows of consecutive levels
+    int nchunks = 0;                     // partial-sum rows per (problem, agent)
+    const size_t part_elems = sweep_part_elems(dtype, B, P, n, K, &part_stride, &nchunks);
+    if (!part_elems) DADMM_FAIL(-2, "unfolded_bwd: P=%d does not fit in shared memory", P);
+    unsigned* slots = (unsigned*)(part + (part_elems * es + 255) / 256 * 256);   // max|adj(y_{k+1})| bits
     const int64_t sn = n, sPn = (int64_t)P * n;
     const size_t row = (size_t)P * 4 * es;
-    const bool with_loss = label && loss_coef;
+    // fused loss term coef[k] (Y[k] - label): coefficients on the host (loss_coef) or on the device (loss_coef_dev)
+    const bool with_loss = label && (loss_coef || loss_coef_dev);
+    const bool dev_coef = label && !loss_coef && loss_coef_dev;
+    auto host_coef = [&](int k) { return (with_loss && !dev_coef) ? loss_coef[k] : 0.0; };
     const bool fused = fused_f16(dtype, algo, B, P, n);
     const size_t wb = fw.w1 + fw.w2;
     f16::Split xs{};
+    char* wsp = (fused && ops && ops->buf) ? (char*)ops->buf : w8;
     DADMM_CUDA(cudaMemsetAsync(ghyp, 0, (size_t)K * row, s));
     if (fused) {
         xs = f16::split_view(w8 + wb, (long long)B * P, n);
         DADMM_CUDA(cudaMemsetAsync(slots, 0, amax_slots_bytes(K), s));
-        if (K > 1)
-            if (int e = fused_prepare(fw, w8, P, n, mf, Wt, fac, s)) return e;
+        if (K > 1 && !(ops && ops->buf && ops->ready))
+            if (int e = fused_prepare(fw, wsp, P, n, mf, Wt, fac, s)) return e;
     }
     {   // adjoint of y_K
         const long long rows = (long long)B * P;
         const int nblk = (int)std::min<long long>(148 * 8, ceil_div64(rows, 8));
         ProfScope prof(PROF_LOSS, s);
-        seed_adjoint_kernel<T><<<nblk, 256, 0, s>>>((const T*)((const char*)Y + (size_t)(K - 1) * NB),
-                                                   gY ? (const T*)((const char*)gY + (size_t)(K - 1) * NB) : nullptr,
-                                                   (with_loss && loss_coef[K - 1] != 0.0) ? (const T*)label : nullptr,
-                                                   (T)(with_loss ? loss_coef[K - 1] : 0.0), B, P, n, (T*)Tb,
-                                                   fused ? slots + (K - 1) : nullptr);
+        DADMM_CUDA(launch_chain(seed_adjoint_kernel<T>, dim3(nblk), dim3(256), 0, s, (const T*)((const char*)Y + (size_t)(K - 1) * NB),
+                                gY ? (const T*)((const char*)gY + (size_t)(K - 1) * NB) : (const T*)nullptr,
+                                (dev_coef || host_coef(K - 1) != 0.0) ? (const T*)label : (const T*)nullptr, (T)host_coef(K - 1),
+                                dev_coef ? loss_coef_dev + (K - 1) : (const double*)nullptr, B, P, n, (T*)Tb,
+                                fused ? slots + (K - 1) : (unsigned*)nullptr));
         DADMM_LAUNCHED();
-    }
-    int nchunks = 0;
-    {
-        StepCfg c;
-        if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return e;
-        nchunks = level_bwd_csplit(B, c.TB, c.nchunks);        // partial-sum rows per (problem, agent)
     }
     for (int k = K - 1; k >= 0; --k) {
         const char* yk = k ? (const char*)Y + (size_t)(k - 1) * NB : (const char*)y0;
@@ -627,17 +655,12 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                                       k ? (const char*)hyp + (k - 1) * row : nullptr, k == K - 1, yk, Uprev, d0,
                                       (const char*)R_save + (size_t)k * NB, Tb, C, ga,
                                       (gY && k) ? (const char*)gY + (size_t)(k - 1) * NB : nullptr, label,
-                                      (with_loss && k) ? loss_coef[k - 1] : 0.0, part, sp, fused ? 1 : 0, s))
+                                      k ? host_coef(k - 1) : 0.0, part + (size_t)k * part_stride * es, sp, fused ? 1 : 0, s,
+                                      (dev_coef && k) ? loss_coef_dev + (k - 1) : nullptr))
             return e;
-        {
-            ProfScope prof(PROF_REDUCE_HYP, s);
-            reduce_level_kernel<T><<<P, 256, 0, s>>>((const T*)part, nchunks, B, P, (T*)((char*)ghyp + k * row),
-                                                    k ? (T*)((char*)ghyp + (k - 1) * row) : nullptr);
-            DADMM_LAUNCHED();
-        }
         if (k > 0) {
             if (fused) {
-                if (int e = fused_contract(fw, w8, B, P, n, mf, (float*)Tb, 1, s, slots + (k - 1), nullptr, algo == DADMM_ALGO_TC_F16X1))
+                if (int e = fused_contract(fw, wsp, w8 + wb, B, P, n, mf, (float*)Tb, 1, s, slots + (k - 1), nullptr, algo == DADMM_ALGO_TC_F16X1))
                     return e;
             } else {
                 if (int e = contract_impl(dtype, algo, B, P, n, n, Wt, (int64_t)n * n, sn, 1, ga, sPn, sn, 1, Tb, sPn, sn, 1, 1, w8, cw, s,
@@ -645,6 +668,11 @@ static int unfolded_bwd_impl(int dtype, int algo, int B, int P, int n, int K, co
                     return e;
             }
         }
+    }
+    {   // all K levels' partial sums -> ghyp [K,P,4]
+        ProfScope prof(PROF_REDUCE_HYP, s);
+        DADMM_CUDA(launch_chain(reduce_levels_kernel<T>, dim3(P, K), dim3(256), 0, s, (const T*)part, part_stride, nchunks, B, P, (T*)ghyp));
+        DADMM_LAUNCHED();
     }
     return 0;
 }
@@ -658,6 +686,12 @@ extern "C" {
 int dadmm_abi_version(void) { return DADMM_ABI_VERSION; }
 const char* dadmm_last_error(void) { return g_err; }
 int64_t dadmm_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dadmm_set_pdl(int on) {
+    const int prev = pdl_enabled() ? 1 : 0;
+    g_pdl.store(on ? 1 : 0);
+    return prev;
+}
 
 int dadmm_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -767,6 +801,11 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
     DADMM_FAIL(-1, "reduce_hyp: unknown dtype %d", dtype);
 }
 
+size_t dadmm_unfolded_op_split_bytes(int dtype, int algo, int B, int P, int n, int m_factor) {
+    const FusedWs f = fused_ws(dtype, algo, B, P, n, m_factor);
+    return f.w1 + f.w2;
+}
+
 int dadmm_unfolded_uses_factor(int dtype, int algo, int B, int P, int n, int m) { return use_factor(dtype, algo, B, P, n, m) ? 1 : 0; }
 
 size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward, int m_factor) {
@@ -775,14 +814,14 @@ size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, 
     const size_t cw = unfolded_cw(dtype, algo, B, P, n, m_factor);
     if (!backward)   // AtAy + two U ping-pong buffers + amax slots + sum-of-squares partials
         return cw + 3 * NBa + amax_slots_bytes(K) + sq_part_bytes(dtype, B, P, n, K);
-    return cw + 3 * NBa + (partials_elems(B, P, n) * es + 255) / 256 * 256 + amax_slots_bytes(K);   // T, C, gAtAy, partials
+    return cw + 3 * NBa + (sweep_part_elems(dtype, B, P, n, K) * es + 255) / 256 * 256 + amax_slots_bytes(K);   // T, C, gAtAy, partials
 }
 
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
                        const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* factor,
                        const void* Atb, const void* y0,
                        const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
-                       int32_t* flags, const dadmm_loss_sums* sums, dadmm_stream_t stream) {
+                       int32_t* flags, const dadmm_loss_sums* sums, const dadmm_op_split* op_split, dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_fwd: bad dims");
     if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
     if (factor && (factor->m <= 0 || !factor->F1 || !factor->F2)) DADMM_FAIL(-1, "unfolded_fwd: bad factor");
@@ -790,12 +829,13 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0, factor ? factor->m : 0))
         DADMM_FAIL(-1, "unfolded_fwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
+    if (int e = check_op_split(op_split, dtype, algo, B, P, n, factor ? factor->m : 0)) return e;
     if (dtype == DADMM_F32)
         return unfolded_fwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
-                                        sums, (cudaStream_t)stream);
+                                        sums, op_split, (cudaStream_t)stream);
     if (dtype == DADMM_F64)
         return unfolded_fwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, W, factor, Atb, y0, U0, d0, Y, U_save, R_save, ws, flags,
-                                         sums, (cudaStream_t)stream);
+                                         sums, op_split, (cudaStream_t)stream);
     DADMM_FAIL(-1, "unfolded_fwd: unknown dtype %d", dtype);
 }
 
@@ -803,8 +843,8 @@ int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const da
                        const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* factor_t,
                        const void* y0, const void* U0,
                        const void* d0, const void* Y, const void* U_save, const void* R_save, const void* gY,
-                       const void* label, const double* loss_coef, void* ghyp, void* ws, size_t ws_bytes,
-                       dadmm_stream_t stream) {
+                       const void* label, const double* loss_coef, const double* loss_coef_dev, void* ghyp, void* ws,
+                       size_t ws_bytes, const dadmm_op_split* op_split, dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_bwd: bad dims");
     if (!clamps || !hyp || !Wt || !y0 || !U0 || !d0 || !Y || !R_save || !ghyp || !ws) DADMM_FAIL(-1, "unfolded_bwd: null pointer");
     if (K > 2 && !U_save) DADMM_FAIL(-1, "unfolded_bwd: U_save required");
@@ -812,12 +852,13 @@ int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const da
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 1, factor_t ? factor_t->m : 0))
         DADMM_FAIL(-1, "unfolded_bwd: workspace too small");
     if (int e = check_graph(graph, P)) return e;
+    if (int e = check_op_split(op_split, dtype, algo, B, P, n, factor_t ? factor_t->m : 0)) return e;
     if (dtype == DADMM_F32)
         return unfolded_bwd_impl<float>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, factor_t, y0, U0, d0, Y, U_save, R_save, gY, label,
-                                        loss_coef, ghyp, ws, (cudaStream_t)stream);
+                                        loss_coef, loss_coef_dev, ghyp, ws, op_split, (cudaStream_t)stream);
     if (dtype == DADMM_F64)
         return unfolded_bwd_impl<double>(dtype, algo, B, P, n, K, graph, clamps, hyp, Wt, factor_t, y0, U0, d0, Y, U_save, R_save, gY, label,
-                                         loss_coef, ghyp, ws, (cudaStream_t)stream);
+                                         loss_coef, loss_coef_dev, ghyp, ws, op_split, (cudaStream_t)stream);
     DADMM_FAIL(-1, "unfolded_bwd: unknown dtype %d", dtype);
 }
 

@@ -142,6 +142,7 @@ struct LevelBwdParams {
     T *Tb, *C, *ga;
     const T *gY_prev, *label;
     T coef_prev;
+    const double* coef_dev;             // optional, device: coefficient of this level's loss term (replaces coef_prev; 0 = no term)
     T* partials;
     SplitOut sp;                        // fp16 split of gAtAy_k; sp.amax_in = max|adj(y_{k+1})|
 };
@@ -298,6 +299,14 @@ level_fwd_kernel(const LevelFwdParams<T> p) {
     __shared__ unsigned sAmax[32];
     __shared__ float sAlpha[32];
 
+    // call-constant inputs (neighbour lists, table rows, degrees) are staged before the dependency wait: this part of the
+    // CTA's life overlaps the tail of the preceding contraction (common.cuh, programmatic dependent launch)
+    const bool staged = p.list_cap > 0;
+    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
+    pdl_wait();
+    pdl_trigger();
+
     // scale of the fused fp16 split of y_{k+1} (identical in every CTA)
     float sc = 1.f;
     bool do_split = false;
@@ -317,9 +326,6 @@ level_fwd_kernel(const LevelFwdParams<T> p) {
     unsigned amax_bits = 0;
     float amax_f = 0.f;
 
-    const bool staged = p.list_cap > 0;
-    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
-    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
     if (first) __syncthreads();                          // (the tile-load barrier below covers the other levels)
     T nonfinite = (T)0;
     const T nG = -p.G, nV = -p.V;
@@ -513,6 +519,22 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
     const bool first = p.first != 0, top = p.top != 0;
     __shared__ float sAlpha[32];
 
+    // call-constant inputs first, then the dependency wait (see level_fwd_kernel)
+    const bool staged = p.list_cap > 0;
+    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
+    for (int r = threadIdx.x; r < R * 4; r += blockDim.x) sAcc[r] = (T)0;
+    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
+    pdl_wait();
+    pdl_trigger();
+
+    // loss term coef * (y_k - label): the coefficient may live on the device (no host round trip in autograd's backward)
+    const T* label = p.label;
+    T coef_prev = p.coef_prev;
+    if (p.coef_dev) {
+        coef_prev = (T)__ldg(p.coef_dev);
+        if (coef_prev == (T)0) label = nullptr;
+    }
+
     // scale of the fused fp16 split of gAtAy_k:  |gAtAy| <= max_p alpha_p * max|adj(y_{k+1})|
     float sc1 = 1.f, sc2 = 1.f;
     bool do_split = false;
@@ -527,10 +549,6 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
         }
     }
 
-    const bool staged = p.list_cap > 0;
-    if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
-    for (int r = threadIdx.x; r < R * 4; r += blockDim.x) sAcc[r] = (T)0;
-    stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
     const T nG = -p.G, nUc = -p.Uc_prev;
 
     for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
@@ -564,7 +582,7 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
         V labv = vzero<T, VEC>();
-        if (p.label) labv = ld_vec<T, VEC>(p.label + ((unsigned)b * p.n + i));
+        if (label) labv = ld_vec<T, VEC>(label + ((unsigned)b * p.n + i));
         struct In { V t, r, u, c; };
         auto issue = [&](int q, In& L) {
             L.c = vzero<T, VEC>();
@@ -618,7 +636,7 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
                 o_c.v[v] = um;
                 o_db.v[v] = rho * rb + eta_prev * um;
                 T dir = zb;
-                if (p.label) dir += p.coef_prev * (y - labv.v[v]);
+                if (label) dir += coef_prev * (y - labv.v[v]);
                 o_dir.v[v] = dir;
             }
             *reinterpret_cast<V*>(tile1 + (unsigned)pp * (CH * (unsigned)sizeof(T)) + lane_bytes) = o_db;
@@ -650,7 +668,7 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
         unsigned char* tile1 = S1 + (size_t)bl * P * CH * sizeof(T);
         const int32_t* lptr = staged ? sPtr + bl * (P + 1) : p.lst_ptr + (p.gid ? __ldg(p.gid + b) : 0) * P;
         const int32_t* lidx = staged ? sIdx + bl * p.list_cap : p.lst_idx;
-        const T* lab = p.label ? p.label + ((unsigned)b * p.n + i) : nullptr;
+        const T* lab = label ? label + ((unsigned)b * p.n + i) : nullptr;
         auto issue = [&](int pp, Row& L) {
             L.t = L.c = L.r = L.u = L.d = L.g = vzero<T, VEC>();
             if (pp < P && act_i) {
@@ -722,7 +740,7 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
                     const T db = rho * rb + eta_prev * um;
                     o_db.v[v] = (mD && act_i) ? db : (T)0;
                     T dir = zb + cur.g.v[v];
-                    if (lab) dir += p.coef_prev * (y - labv.v[v]);
+                    if (lab) dir += coef_prev * (y - labv.v[v]);
                     o_dir.v[v] = dir;
                 }
             }
@@ -782,11 +800,18 @@ level_bwd_kernel(const LevelBwdParams<T> p) {
     }
 }
 
-// hyper-parameter gradient rows from the level partials [nchunks][B][P][4] = (d alpha_k, d tau_k, d rho_k, d eta_{k-1})
+// hyper-parameter gradient rows from the level partials [K][nchunks][B][P][4] = (d alpha_k, d tau_k, d rho_k, d eta_{k-1}):
+// ONE launch after the reverse sweep, CTA (p, k) finishes agent p of level k (the per-level launches this replaces sat
+// on the critical path between a backward level and its contraction; the sums and their order are the same)
 template <typename T>
-__global__ void __launch_bounds__(256) reduce_level_kernel(const T* __restrict__ part, int nchunks, int B, int P,
-                                                           T* row_k, T* row_prev) {
-    const int pp = blockIdx.x;
+__global__ void __launch_bounds__(256) reduce_levels_kernel(const T* __restrict__ part, size_t level_stride, int nchunks, int B,
+                                                            int P, T* __restrict__ ghyp) {
+    pdl_wait();
+    pdl_trigger();
+    const int pp = blockIdx.x, k = blockIdx.y;
+    part += (size_t)k * level_stride;
+    T* row_k = ghyp + (size_t)k * P * 4;
+    T* row_prev = k ? row_k - (size_t)P * 4 : nullptr;
     double acc[4] = {0, 0, 0, 0};
     const long long rows = (long long)nchunks * B;
     for (long long rI = threadIdx.x; rI < rows; rI += blockDim.x) {
@@ -813,6 +838,8 @@ __global__ void __launch_bounds__(256) reduce_level_kernel(const T* __restrict__
 // sumsq[k] = sum of the per-CTA partials the forward level k left in part[k][0..grid), for k = k_first + blockIdx.x
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restrict__ part, size_t row_stride, int grid, int k_first,
                                                           double* __restrict__ sumsq) {
+    pdl_wait();
+    pdl_trigger();
     const int k = k_first + blockIdx.x;
     double a = 0;
     for (int i = threadIdx.x; i < grid; i += blockDim.x) a += part[(size_t)k * row_stride + i];
@@ -873,8 +900,14 @@ __global__ void __launch_bounds__(256) loss_sums_final_kernel(const double* __re
 // T = gY_last + coef * (Y_last - label): adjoint of y_K entering the reverse sweep
 template <typename T>
 __global__ void __launch_bounds__(256) seed_adjoint_kernel(const T* __restrict__ Ylast, const T* __restrict__ gYlast,
-                                                           const T* __restrict__ label, T coef, int B, int P, int n,
-                                                           T* __restrict__ out, unsigned* amax_out) {
+                                                           const T* __restrict__ label, T coef, const double* __restrict__ coef_dev,
+                                                           int B, int P, int n, T* __restrict__ out, unsigned* amax_out) {
+    pdl_wait();
+    pdl_trigger();
+    if (coef_dev) {                      // device-side coefficient (see LevelBwdParams::coef_dev)
+        coef = (T)__ldg(coef_dev);
+        if (coef == (T)0) label = nullptr;
+    }
     const long long rows = (long long)B * P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     __shared__ unsigned sAmax[32];

@@ -14,7 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
@@ -47,6 +47,11 @@ class LossSums(C.Structure):
     _fields_ = [("agent_sum", C.c_void_p), ("sumsq", C.c_void_p), ("valid", C.POINTER(C.c_int32))]
 
 
+class OpSplit(C.Structure):
+    """Persistent home of the operator's tensor-core operand copies (``dadmm_op_split``)."""
+    _fields_ = [("buf", C.c_void_p), ("bytes", C.c_size_t), ("ready", C.c_int32)]
+
+
 class DadmmError(RuntimeError):
     pass
 
@@ -59,11 +64,13 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     i32, i64, vp, dbl, sz = C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_size_t
     GP, CP, HP, FP, SP = C.POINTER(Graph), C.POINTER(Clamps), C.POINTER(Hyp), C.POINTER(Factor), C.POINTER(LossSums)
+    OP = C.POINTER(OpSplit)
     sigs = {
         "dadmm_abi_version": (i32, []),
         "dadmm_last_error": (C.c_char_p, []),
         "dadmm_device_check": (i32, []),
         "dadmm_launch_count": (i64, []),
+        "dadmm_set_pdl": (i32, [i32]),
         "dadmm_profile_enable": (i32, [i32]),
         "dadmm_profile_read": (i32, [C.POINTER(dbl), C.POINTER(i64)]),
         "dadmm_contract": (i32, [i32, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
@@ -76,9 +83,10 @@ def _load():
         "dadmm_partials_elems": (sz, [i32, i32, i32, i32]),
         "dadmm_reduce_hyp": (i32, [i32, i32, i32, i32, vp, i32, vp, i64, i64, i64, i32, vp]),
         "dadmm_unfolded_fwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp, sz,
-                                     vp, SP, vp]),
+                                     vp, SP, OP, vp]),
         "dadmm_unfolded_bwd": (i32, [i32, i32, i32, i32, i32, i32, GP, CP, vp, vp, FP, vp, vp, vp, vp, vp, vp, vp, vp,
-                                     C.POINTER(dbl), vp, vp, sz, vp]),
+                                     C.POINTER(dbl), vp, vp, vp, sz, OP, vp]),
+        "dadmm_unfolded_op_split_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
         "dadmm_unfolded_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32, i32, i32]),
         "dadmm_unfolded_uses_factor": (i32, [i32, i32, i32, i32, i32, i32]),
         "dadmm_loss_fwd": (i32, [i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, sz, vp]),
@@ -148,6 +156,11 @@ def ptr(t: Optional[torch.Tensor]):
 
 def stream_ptr(dev) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch of the K-loop chain on/off (``dadmm_set_pdl``); returns the previous setting."""
+    return bool(lib.dadmm_set_pdl(int(bool(on))))
 
 
 def launch_count() -> int:

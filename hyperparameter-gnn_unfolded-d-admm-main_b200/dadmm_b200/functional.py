@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -208,6 +210,47 @@ def _factor_struct(factor, P, n, like):
     return _lib.Factor(int(m), ptr(F1), ptr(F2), ptr(rhs)), (F1, F2, rhs)
 
 
+class _OpSplitCache:
+    """Persistent operator splits (``dadmm_op_split``).  The reference's operator is a constructor-time constant
+    (unfolded_DLASSO.py:12-16), so the scaled fp16 hi/lo copies the tensor-core contraction reads are made once per
+    (operator storage, version, route, stream) instead of by every forward pass and every reverse sweep.  An in-place
+    update of the operator bumps its version counter and invalidates the entry; ``DADMM_OP_SPLIT_CACHE=0`` disables it."""
+    MAX = 4
+
+    def __init__(self):
+        self.entries = OrderedDict()
+        self.enabled = os.environ.get("DADMM_OP_SPLIT_CACHE", "1") != "0"
+
+    def lookup(self, dev, dt, al, B, P, n, W, fac):
+        """-> [buffer, ready, keepalive] or None when the shape does not take the fused tensor-core path."""
+        if not self.enabled:
+            return None
+        m = int(fac[0].m) if fac else 0
+        nbytes = int(lib.dadmm_unfolded_op_split_bytes(dt, al, B, P, n, m))
+        if nbytes == 0:
+            return None
+        two = bool(m and lib.dadmm_unfolded_uses_factor(dt, al, B, P, n, m))
+        src = tuple(fac[1][:2]) if two else (W,)
+        key = (two, nbytes, str(dev), torch.cuda.current_stream(dev).cuda_stream,
+               tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())) for t in src))
+        ent = self.entries.get(key)
+        if ent is None:
+            ent = [torch.empty(nbytes, dtype=torch.uint8, device=dev), False, src]      # src: the storage cannot be recycled while cached
+            self.entries[key] = ent
+            while len(self.entries) > self.MAX:
+                self.entries.popitem(last=False)
+        else:
+            self.entries.move_to_end(key)
+        return ent
+
+    @staticmethod
+    def struct(ent):
+        return None if ent is None else _lib.OpSplit(ent[0].data_ptr(), ent[0].numel(), int(ent[1]))
+
+
+_op_splits = _OpSplitCache()
+
+
 class Unfolded(torch.autograd.Function):
     """K fused iterations of model #1: hyp [K,P,4] -> Y [K,B,P,n].  Saves Y, U_k and the raw
     gradients r_k; backward runs the reverse sweep on device and returns d/d hyp only (the
@@ -240,10 +283,16 @@ class Unfolded(torch.autograd.Function):
         with device_guard(dev):
             wsb = lib.dadmm_unfolded_ws_bytes(dt, al, B, P, n, K, 0, fac[0].m if fac else 0)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            W = W.contiguous()
+            ent = _op_splits.lookup(dev, dt, al, B, P, n, W, fac)
+            ops = _OpSplitCache.struct(ent)
             check(lib.dadmm_unfolded_fwd(dt, al, B, P, n, K, C.byref(graph.c), carr, ptr(hyp), ptr(W),
                                          C.byref(fac[0]) if fac else None, ptr(Atb), ptr(y0),
                                          ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(ws), wsb, ptr(flags),
-                                         C.byref(sums[0]) if sums else None, stream_ptr(dev)), "dadmm_unfolded_fwd")
+                                         C.byref(sums[0]) if sums else None, C.byref(ops) if ops else None,
+                                         stream_ptr(dev)), "dadmm_unfolded_fwd")
+            if ent is not None:
+                ent[1] = True
         if sums is not None and any(sums[3]):
             handle.sums = (sums[1], sums[2], [bool(v) for v in sums[3]], Y.data_ptr())
         if need_grad:
@@ -259,11 +308,14 @@ class Unfolded(torch.autograd.Function):
         dev = Y.device
         K, B, P, n = Y.shape[:4]
         dt = dtype_code(Y)
-        label, coef = None, None
+        label, coef, coef_dev = None, None, None
         fused = ctx.handle.take() if ctx.handle is not None else None
         if fused is not None:
             label, coefs, sentinel = fused
-            coef = (C.c_double * K)(*coefs)
+            if isinstance(coefs, torch.Tensor):
+                coef_dev = coefs.to(device=dev, dtype=torch.float64).contiguous()      # stays on the device: no host sync
+            else:
+                coef = (C.c_double * K)(*coefs)
             if gY is not None and gY.data_ptr() == sentinel.data_ptr():
                 gY = None       # zero placeholder emitted by MSELoss.backward: gradient arrives through (label, coef)
         if gY is not None:
@@ -273,10 +325,15 @@ class Unfolded(torch.autograd.Function):
         with device_guard(dev):
             wsb = lib.dadmm_unfolded_ws_bytes(dt, ctx.algo, B, P, n, K, 1, fac_t[0].m if fac_t else 0)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            Wt = Wt.contiguous()
+            ent = _op_splits.lookup(dev, dt, ctx.algo, B, P, n, Wt, fac_t) if K > 1 else None
+            ops = _OpSplitCache.struct(ent)
             check(lib.dadmm_unfolded_bwd(dt, ctx.algo, B, P, n, K, C.byref(ctx.graph.c), ctx.clamps, ptr(hyp), ptr(Wt),
                                          C.byref(fac_t[0]) if fac_t else None, ptr(y0), ptr(U0), ptr(d0), ptr(Y), ptr(U_save), ptr(R_save), ptr(gY),
-                                         ptr(label), coef, ptr(ghyp), ptr(ws), wsb, stream_ptr(dev)),
-                  "dadmm_unfolded_bwd")
+                                         ptr(label), coef, ptr(coef_dev), ptr(ghyp), ptr(ws), wsb, C.byref(ops) if ops else None,
+                                         stream_ptr(dev)), "dadmm_unfolded_bwd")
+            if ent is not None:
+                ent[1] = True
         return (ghyp,) + (None,) * 13
 
 
@@ -360,11 +417,14 @@ class MSELoss(torch.autograd.Function):
         Y, label = ctx.saved_tensors
         K, B, P, n = Y.shape[:4]
         scale = 2.0 / (P * (ctx.B_norm or B) * n)
-        coefs = [float(v) * scale for v in g_losses.detach().to("cpu", torch.float64).tolist()]
         if ctx.handle is not None:
+            # coefficients stay on the device (dadmm_unfolded_bwd: loss_coef_dev): reading them here would stall the host
+            # until the whole forward pass has drained, once per training step
+            coefs_dev = g_losses.detach().to(torch.float64) * scale
             sentinel = torch.zeros((), dtype=Y.dtype, device=Y.device).expand(Y.shape)
-            if ctx.handle.offer(label.contiguous(), coefs, sentinel):
+            if ctx.handle.offer(label.contiguous(), coefs_dev, sentinel):
                 return sentinel, None, None, None
+        coefs = [float(v) * scale for v in g_losses.detach().to("cpu", torch.float64).tolist()]
         gY = torch.empty_like(Y, memory_format=torch.contiguous_format)
         with device_guard(Y.device):
             check(lib.dadmm_loss_bwd(dtype_code(Y), K, B, P, n, ptr(Y.contiguous()), ptr(label.contiguous()),

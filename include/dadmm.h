@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 4
+#define DADMM_ABI_VERSION 5
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -127,6 +127,12 @@ int dadmm_device_check(void);
 /* number of kernels launched by this library since load (all threads) */
 int64_t dadmm_launch_count(void);
 
+/* Programmatic dependent launch of the K-loop's kernel chain (on by default; DADMM_PDL=0 in the environment starts
+ * with it off): each kernel of the chain is scheduled while its predecessor drains and waits on the device
+ * (griddepcontrol.wait) before touching anything the predecessor produces.  Results are bit-identical either way;
+ * the switch exists for A/B timing and tests.  Returns the previous setting. */
+int dadmm_set_pdl(int on);
+
 /* Per-kernel-kind timing for bench.py's roofline: after dadmm_profile_enable(1) every launch is bracketed
  * by CUDA events on its stream; dadmm_profile_read sums elapsed ms / launch counts per kind
  * (0 contract SIMT, 1 contract tcgen05, 2 step fwd, 3 step bwd, 4 reduce_hyp, 5 loss, 6 operand split,
@@ -183,6 +189,20 @@ int dadmm_reduce_hyp(int dtype, int B, int P, int n, const void* ghyp_partials, 
                      void* ghyp, int64_t stride_b, int64_t stride_p, int64_t stride_c,
                      int accumulate, dadmm_stream_t stream);
 
+/* Optional persistent home of the operator's tensor-core operand copies (the scaled fp16 hi/lo split of W, or of the
+ * factor pair).  The operator of the reference is a constructor-time constant (unfolded_DLASSO.py:12-16 computes AtA
+ * once), so its split need not be redone by every forward and every reverse sweep: with ready == 0 the call fills
+ * `buf` (dadmm_unfolded_op_split_bytes() bytes, 256-byte aligned) instead of its workspace head, with ready == 1 it
+ * reuses the contents.  The split depends on (W | factor F1,F2) and on the route dadmm_unfolded_uses_factor() reports;
+ * the forward's and the reverse sweep's splits are the same when Wt and factor_t alias W and factor.  NULL (or a NULL
+ * buf, or a shape that does not take the fused tensor-core path: 0 bytes) keeps everything in the workspace. */
+typedef struct dadmm_op_split {
+    void* buf;
+    size_t bytes;
+    int ready;
+} dadmm_op_split;
+size_t dadmm_unfolded_op_split_bytes(int dtype, int algo, int B, int P, int n, int m_factor);
+
 /* K iterations of model #1 (hyp [K,P,4] shared over the batch, clamps[K] on the host):
  * Y[k] = y_{k+1}; U_save[k] = U_{k+1} and R_save[k] = r_k are written when non-NULL (training).
  * W = AtA [P,n,n]; factor (may be NULL) = its factorisation.  ws >= dadmm_unfolded_ws_bytes(). */
@@ -191,16 +211,21 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
                        const void* Atb,
                        const void* y0, const void* U0, const void* d0,
                        void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
-                       int32_t* flags, const dadmm_loss_sums* sums /* may be NULL */, dadmm_stream_t stream);
+                       int32_t* flags, const dadmm_loss_sums* sums /* may be NULL */,
+                       const dadmm_op_split* op_split /* may be NULL */, dadmm_stream_t stream);
 /* Reverse sweep: gY [K,B,P,n] dense upstream gradient (may be NULL) and/or the fused loss term
- * loss_coef[k]*(Y[k]-label) (label [B,n], loss_coef host [K], both may be NULL).  Wt = AtA^T [P,n,n];
- * factor_t (may be NULL) factorises Wt (for the symmetric AtA: the forward's factor).  Writes ghyp [K,P,4]. */
+ * coef[k]*(Y[k]-label) with label [B,n] and the K coefficients either on the host (loss_coef) or on the
+ * device (loss_coef_dev, doubles; used when loss_coef == NULL -- autograd hands d loss / d losses[k] over
+ * as a device tensor, and reading it on the host would drain the stream in the middle of every training
+ * step).  A zero coefficient means "no term" either way.  Wt = AtA^T [P,n,n]; factor_t (may be NULL)
+ * factorises Wt (for the symmetric AtA: the forward's factor).  Writes ghyp [K,P,4]. */
 int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
                        const dadmm_clamps* clamps, const void* hyp, const void* Wt, const dadmm_factor* factor_t,
                        const void* y0, const void* U0, const void* d0,
                        const void* Y, const void* U_save, const void* R_save,
-                       const void* gY, const void* label, const double* loss_coef,
-                       void* ghyp, void* ws, size_t ws_bytes, dadmm_stream_t stream);
+                       const void* gY, const void* label, const double* loss_coef, const double* loss_coef_dev,
+                       void* ghyp, void* ws, size_t ws_bytes, const dadmm_op_split* op_split /* may be NULL */,
+                       dadmm_stream_t stream);
 /* m_factor = factor->m of the call (0: no factor) */
 size_t dadmm_unfolded_ws_bytes(int dtype, int algo, int B, int P, int n, int K, int backward, int m_factor);
 /* 1 when the fused path would evaluate the contraction in two stages for this shape and inner dimension m */
