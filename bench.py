@@ -384,23 +384,33 @@ def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False):
     prof = dict(prof)
     if prof.get("contract_stage1", (0, 0))[1]:          # two-stage contraction: both launches belong to the contraction
         prof["contract_tc"] = (prof["contract_tc"][0] + prof["contract_stage1"][0], prof["contract_tc"][1] + prof["contract_stage1"][1])
-    kind = max(("contract_simt", "contract_tc", "step_fwd", "step_bwd"), key=lambda k: prof[k][0])
-    ms, cnt = prof[kind]
-    if kind.startswith("contract"):
-        flops = 2.0 * P * (w["m"] if two_stage else n) * n * B_loc
-        ach = flops / (ms / cnt * 1e-3) / 1e12
-        note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). The default kernel "
-                "issues 3 fp16 MMAs per product (scaled hi/lo operand pairs), so 1/3 of this peak is its ceiling "
-                "(3xTF32: 1/6; the SIMT kernel's ceiling is the FP32 FMA pipe, ~60-70 TFLOP/s)")
-        roof = {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
-                "share_of_step": ms / t_step_ms, "note": note}
-    else:
+    def describe(kind):
+        ms, cnt = prof[kind]
+        if kind.startswith("contract"):
+            flops = 2.0 * P * (w["m"] if two_stage else n) * n * B_loc
+            ach = flops / (ms / cnt * 1e-3) / 1e12
+            note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). The default kernel "
+                    "issues 3 fp16 MMAs per product (scaled hi/lo operand pairs), so 1/3 of this peak is its ceiling "
+                    "(3xTF32: 1/6; the SIMT kernel's ceiling is the FP32 FMA pipe, ~60-70 TFLOP/s)")
+            return {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
+                    "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
+                    "share_of_step": ms / t_step_ms, "note": note}
         per = (20 if kind == "step_fwd" else 36) * P * n * B_loc
         ach = per / (ms / cnt * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+        return {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
                 "share_of_step": ms / t_step_ms}
+
+    # Dominant kernel.  At config 4 the two launches of the contraction together and the backward level each take a third
+    # of the step and swap places from run to run, so shares within 5 % of each other count as a tie and the tie goes to
+    # the HBM-bound level kernel (the resource BASELINE.json's metric names); the other one is reported beside it.
+    best_c = max(("contract_simt", "contract_tc"), key=lambda k: prof[k][0])
+    best_s = max(("step_fwd", "step_bwd"), key=lambda k: prof[k][0])
+    kind, other = (best_c, best_s) if prof[best_c][0] > 1.05 * prof[best_s][0] else (best_s, best_c)
+    roof = describe(kind)
+    roof["tie_rule"] = "shares within 5 % are a tie; ties go to the HBM-bound level kernel"
+    if prof[other][1]:
+        roof["runner_up"] = {k: v for k, v in describe(other).items() if k not in ("note", "peak_source", "traffic")}
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (same workload / batch)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
