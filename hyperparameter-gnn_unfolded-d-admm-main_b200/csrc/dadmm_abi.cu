@@ -823,8 +823,11 @@ int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const da
                        const void* U0, const void* d0, void* Y, void* U_save, void* R_save, void* ws, size_t ws_bytes,
                        int32_t* flags, const dadmm_loss_sums* sums, const dadmm_op_split* op_split, dadmm_stream_t stream) {
     if (B <= 0 || P <= 0 || n <= 0 || K <= 0) DADMM_FAIL(-1, "unfolded_fwd: bad dims");
-    if (!clamps || !hyp || !W || !Atb || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
+    if (!clamps || !hyp || !W || !y0 || !U0 || !d0 || !Y || !ws) DADMM_FAIL(-1, "unfolded_fwd: null pointer");
     if (factor && (factor->m <= 0 || !factor->F1 || !factor->F2)) DADMM_FAIL(-1, "unfolded_fwd: bad factor");
+    // Atb may be omitted only where it is never read: the two-stage route with the observation term riding in stage 1
+    if (!Atb && !(factor && factor->rhs && use_factor(dtype, algo, B, P, n, factor->m)))
+        DADMM_FAIL(-1, "unfolded_fwd: Atb is required (NULL only with factor->rhs on the two-stage route)");
     if (sums && (!sums->agent_sum || !sums->sumsq || !sums->valid)) DADMM_FAIL(-1, "unfolded_fwd: bad loss-sums descriptor");
     if (ws_bytes < dadmm_unfolded_ws_bytes(dtype, algo, B, P, n, K, 0, factor ? factor->m : 0))
         DADMM_FAIL(-1, "unfolded_fwd: workspace too small");

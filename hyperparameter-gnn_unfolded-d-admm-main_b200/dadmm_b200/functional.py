@@ -262,7 +262,8 @@ class Unfolded(torch.autograd.Function):
         (``dadmm_factor``): lets the library evaluate the contraction in two stages when that is cheaper
         (AtA = A^T A: F1 = A, F2 = A^T, rhs = b)."""
         dev = require_cuda(hyp, W, Atb, y0, U0, d0)
-        hyp, Atb, y0, U0, d0 = (t.contiguous() for t in (hyp, Atb, y0, U0, d0))
+        hyp, y0, U0, d0 = (t.contiguous() for t in (hyp, y0, U0, d0))
+        Atb = Atb.contiguous() if Atb is not None else None      # None: only with a factor rhs on the two-stage route
         K, P, _ = hyp.shape
         B, _, n = y0.shape
         dt, al = dtype_code(y0), _algo(algo)

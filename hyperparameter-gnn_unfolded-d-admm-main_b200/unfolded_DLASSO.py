@@ -19,6 +19,33 @@ from dadmm_b200 import functional as DF
 from dadmm_b200.graph import BatchGraph
 
 
+class _PrefixSums(torch.autograd.Function):
+    """s[k] = torch.sum(param[:k+1], dim=0), k < K  (unfolded_DLASSO.py:157).  Forward keeps the reference's reduction call
+    by call, so the rows agree bit for bit; backward is the closed form d param[i] = sum_{k >= i} d s[k] as one masked
+    product and one reduction instead of the ~3K tiny slice-backward / accumulate kernels autograd chains up behind K
+    slices -- at small per-GPU batches those launches were a measurable share of the step."""
+
+    _masks = {}
+
+    @staticmethod
+    def forward(ctx, param, K):
+        ctx.rows, ctx.K = param.shape[0], K
+        return torch.stack([torch.sum(param[:k + 1], dim=0) for k in range(K)])
+
+    @staticmethod
+    def backward(ctx, gs):
+        K = ctx.K
+        key = (K, gs.device, gs.dtype)
+        mask = _PrefixSums._masks.get(key)
+        if mask is None:
+            mask = torch.triu(torch.ones((K, K), dtype=gs.dtype, device=gs.device))      # mask[i, k] = 1 for k >= i
+            _PrefixSums._masks[key] = mask
+        g = (mask.reshape(K, K, *([1] * (gs.dim() - 1))) * gs.unsqueeze(0)).sum(dim=1)
+        if ctx.rows > K:
+            g = torch.cat([g, g.new_zeros((ctx.rows - K,) + tuple(g.shape[1:]))])
+        return g, None
+
+
 class seq_hyperparam(nn.Module):
     """Learned per-iteration hyper-parameters (alpha, tau, rho, eta): ``param`` [K, P|1, 4], zero-init."""
 
@@ -44,8 +71,7 @@ class seq_hyperparam(nn.Module):
     def table(self, K):
         """All K rows at once, [K, P|1, 4]: row k == forward(k).squeeze(-1).  The running sum uses the same
         ``torch.sum(param[:k+1])`` reduction as the reference so the rows agree bit for bit."""
-        s = torch.stack([torch.sum(self.param[:k + 1], dim=0) for k in range(K)])
-        return self._squash(s)
+        return self._squash(_PrefixSums.apply(self.param, K))
 
 
 class DLASSO_unfolded(nn.Module):
@@ -94,7 +120,8 @@ class DLASSO_unfolded(nn.Module):
         K = self.K if K is None else min(K, self.K)
         DF.require_cuda(b)
         A, W, Wt, At = self._operators(device)
-        Atb = DF.contract(At, b.to(W.dtype).squeeze(-1), algo=self.contract_algo)          # A_p^T b_p  (reference :45)
+        # A_p^T b_p (reference :45) -- not needed when the library forms the residual as A^T (A y - b) from the factor pair
+        Atb = None if self._residual_from_factor(W, batch_size) else self._atb(At, b, W.dtype)
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         # initial noise: same three draws, same order / shape / device as the reference (:49-51)
         y0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
@@ -103,6 +130,17 @@ class DLASSO_unfolded(nn.Module):
         table = self.seq_hyp.table(K)                                   # [K, P|1, 4]
         Y = self._run(table, W, Wt, Atb, y0, U0, d0, graph, K, b)
         return Y, table[K - 1].unsqueeze(-1)
+
+    def _atb(self, At, b, dtype):
+        return DF.contract(At, b.to(dtype).squeeze(-1), algo=self.contract_algo)
+
+    def _residual_from_factor(self, W, batch_size):
+        """True when ``_run`` will hand (A, A^T, b) to the library AND the library takes the two-stage route for this
+        shape (``dadmm_unfolded_uses_factor``): the forward then never reads ``Atb``."""
+        if not (self.two_stage and W.dtype == torch.float32 and getattr(self, "two_stage_rhs", True)):
+            return False
+        return bool(DF.lib.dadmm_unfolded_uses_factor(DF.dtype_code(W), DF._algo(self.contract_algo), batch_size, self.P,
+                                                      self.n, self.m))
 
     def _run(self, table, W, Wt, Atb, y0, U0, d0, graph, K, b=None):
         hyp = table.expand(K, self.P, 4).contiguous().to(W.dtype)
@@ -120,6 +158,8 @@ class DLASSO_unfolded(nn.Module):
         if flags is not None and bool(flags.any()):
             # non-finite values seen: redo the batch on the guarded path, which reproduces the reference's
             # reset / skip semantics (:55-61, :84-86, :102-104) iteration by iteration
+            if Atb is None:
+                Atb = self._atb(self._operators(W.device)[3], b, W.dtype)
             return self._run_guarded(hyp, W, Wt, Atb, y0, U0, d0, graph, K)
         Y._dadmm_handle = handle
         return Y

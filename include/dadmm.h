@@ -205,7 +205,9 @@ size_t dadmm_unfolded_op_split_bytes(int dtype, int algo, int B, int P, int n, i
 
 /* K iterations of model #1 (hyp [K,P,4] shared over the batch, clamps[K] on the host):
  * Y[k] = y_{k+1}; U_save[k] = U_{k+1} and R_save[k] = r_k are written when non-NULL (training).
- * W = AtA [P,n,n]; factor (may be NULL) = its factorisation.  ws >= dadmm_unfolded_ws_bytes(). */
+ * W = AtA [P,n,n]; factor (may be NULL) = its factorisation.  Atb [B,P,n] may be NULL only when it is never read:
+ * factor->rhs given and dadmm_unfolded_uses_factor() == 1 (the residual is then formed as F2 (F1 y - rhs)).
+ * ws >= dadmm_unfolded_ws_bytes(). */
 int dadmm_unfolded_fwd(int dtype, int algo, int B, int P, int n, int K, const dadmm_graph* graph,
                        const dadmm_clamps* clamps, const void* hyp, const void* W, const dadmm_factor* factor,
                        const void* Atb,

@@ -289,3 +289,28 @@ def test_graph_ingestion_rejects_foreign_nodes():
     h.add_nodes_from(range(3))
     with pytest.raises(ValueError, match="no node 3"):
         G.HostGraph([h], 4)
+
+
+def test_hyper_parameter_table_backward_closed_form_matches_autograd():
+    """seq_hyperparam.table: rows bit-identical to the per-k torch.sum of the reference (unfolded_DLASSO.py:157); its
+    backward (one masked product + one reduction) equals autograd through the K slices, also when K < len(param)."""
+    import argparse
+    import unfolded_DLASSO as U
+    args = argparse.Namespace(max_penalty_threshold=0.8, penalty_reduction_factor=0.95)
+    mp = torch.tensor([0.1, 0.99, 0.99, 0.99])
+    for shape, K in (([25, 50, 4], 25), ([15, 1, 4], 15), ([15, 5, 4], 9)):
+        torch.manual_seed(K)
+        sh = U.seq_hyperparam(shape, mp, args).double()
+        with torch.no_grad():
+            sh.param.copy_(torch.randn(shape) * 0.7)
+        w = torch.randn((K, shape[1], 4), dtype=torch.float64)
+        t = sh.table(K)
+        (t * w).sum().backward()
+        g_closed, sh.param.grad = sh.param.grad.clone(), None
+        t_ref = sh._squash(torch.stack([torch.sum(sh.param[:k + 1], dim=0) for k in range(K)]))
+        (t_ref * w).sum().backward()
+        assert torch.equal(t, t_ref)
+        assert g_closed.shape == sh.param.shape
+        assert float((g_closed - sh.param.grad).abs().max()) < 1e-14
+        if K < shape[0]:
+            assert float(g_closed[K:].abs().max()) == 0.0

@@ -164,3 +164,75 @@ def test_operator_split_cache_reuse_and_invalidation():
         assert torch.equal(a, b)
     assert not torch.equal(changed[0], first[0])
     assert len(cache.entries) == 2
+
+
+def _module_case(P=3, n=512, m=160, B=256, K=6, seed=31):
+    import argparse
+    import unfolded_DLASSO
+    pr = random_problem(P, n, m, B, K, seed=seed, a_scale=0.1)
+    args = argparse.Namespace(m=m, n=n, P=P, GHN_iter_num=K, DADMM_mode="diff", alpha_max=0.1, tau_max=0.99, rho_max=0.99,
+                              eta_max=0.99, max_penalty_threshold=0.8, penalty_reduction_factor=0.95, batch_size=B, snr=4)
+    model = unfolded_DLASSO.DLASSO_unfolded(pr["A"].to(DEV), args).to(DEV)
+    with torch.no_grad():
+        model.seq_hyp.param.copy_(pr["param"])
+    return model, pr
+
+
+def test_module_skips_the_unused_Atb_on_the_two_stage_route(capsys):
+    """When the library forms the residual as A^T (A y - b), the module no longer computes A^T b: results equal the route
+    that subtracts a precomputed Atb to fp32 rounding, gradients included; and a NaN batch still reaches the guarded
+    path (which needs Atb and computes it on demand)."""
+    import gnn_dlasso_utils
+    model, pr = _module_case()
+    W = model._operators(torch.device(DEV))[1]
+    assert model._residual_from_factor(W, len(pr["b"]))
+    outs = []
+    for rhs in (True, False):
+        model.two_stage_rhs = rhs
+        model.zero_grad()
+        torch.manual_seed(2)
+        Y, _ = model(pr["b"].to(DEV), pr["graphs"])
+        _, lf = gnn_dlasso_utils.compute_loss(Y, pr["label"].to(DEV))
+        lf.backward()
+        outs.append((Y.detach().clone(), model.seq_hyp.param.grad.clone()))
+    assert rel_l2(outs[0][0], outs[1][0]) < 1e-5 and rel_l2(outs[0][1], outs[1][1]) < 1e-4
+    assert not torch.equal(outs[0][0], outs[1][0])          # really two different evaluation routes
+    model.two_stage_rhs = True
+    b = pr["b"].clone()
+    b[1, 2, 0, 0] = float("nan")
+    Y, _ = model(b.to(DEV), pr["graphs"])
+    assert "NaN/Inf in gradient at iteration 0" in capsys.readouterr().out
+    assert torch.isfinite(Y).all()
+
+
+def test_training_steps_through_the_modules_are_reproducible_and_sync_free_in_backward():
+    """Two identical 3-step Adam runs through the drop-in module (table -> Unfolded -> compute_loss -> backward -> step)
+    give bit-identical parameters; the backward of a step enqueues without a host read of the loss gradient (the device
+    coefficient path is the one taken: the side channel carries a tensor)."""
+    import gnn_dlasso_utils
+    from dadmm_b200 import functional as DF
+    seen = []
+    offer = DF.FusedLossHandle.offer
+
+    def spy(self, label, coefs, sentinel):
+        seen.append(type(coefs))
+        return offer(self, label, coefs, sentinel)
+    DF.FusedLossHandle.offer = spy
+    try:
+        finals = []
+        for rep in range(2):
+            model, pr = _module_case(K=5, seed=37)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+            b, label = pr["b"].to(DEV), pr["label"].to(DEV)
+            for step in range(3):
+                torch.manual_seed(100 + step)
+                Y, _ = model(b, pr["graphs"])
+                _, lf = gnn_dlasso_utils.compute_loss(Y, label, check_finite=False)
+                opt.zero_grad(set_to_none=True)
+                lf.backward()
+                opt.step()
+            finals.append(model.seq_hyp.param.detach().clone())
+    finally:
+        DF.FusedLossHandle.offer = offer
+    assert torch.equal(finals[0], finals[1])
+    assert seen and all(t is torch.Tensor for t in seen)
