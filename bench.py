@@ -191,7 +191,8 @@ def run_reference_arm(opt, w):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "batch_in_sample": B_ref},
+            "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": w["B"],
+                       "batch_in_sample": B_ref},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

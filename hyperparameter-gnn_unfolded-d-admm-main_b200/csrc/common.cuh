@@ -169,6 +169,17 @@ inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Function attributes (dynamic shared-memory limits) are per device: `first()` is true once per device of the process
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> seen{0};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        return !(seen.fetch_or(bit) & bit);
+    }
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div64(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -562,11 +562,9 @@ inline int launch_nt(Params& p, const Split& x, int n_in, int B, int P, tc::Enco
     if (int e = encode3(enc, &mxl, x.lo, n_in, P, B, np * 2, (cuuint64_t)P * np * 2, BKE, 1, G::XROWS)) return e;
     p.n_tiles = ceil_div(B, NT);
     p.total_tiles = P * p.m_tiles * p.n_tiles;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first())
         DADMM_CUDA(cudaFuncSetAttribute(contract_f16_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-        attr_set = true;
-    }
     const int clusters = std::min(num_sms / 2, p.total_tiles);
     ProfScope prof(stage1 ? PROF_CONTRACT_STAGE1 : PROF_CONTRACT_TC, s);
     DADMM_CUDA(launch_chain(contract_f16_kernel<NT>, dim3(2 * clusters), dim3(THREADS), (size_t)G::SMEM, s, mwh, mwl, mxh, mxl, p));

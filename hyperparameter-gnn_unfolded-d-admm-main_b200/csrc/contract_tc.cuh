@@ -658,11 +658,10 @@ inline int launch(int B, int P, int n_out, int n_in, const float* W, const float
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         DADMM_CUDA(cudaFuncSetAttribute(contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         DADMM_CUDA(cudaFuncSetAttribute(contract_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
-        attr_set = true;
     }
     ProfScope prof(PROF_CONTRACT_TC, s);
     if (pair) {
