@@ -72,6 +72,36 @@ def _ema_weights(B, mom, device, dtype):
     return w
 
 
+class _PerSampleBatchNorm(torch.autograd.Function):
+    """Training-mode ``BatchNorm1d`` applied to every sample's [P,C] block of x [B,P,C] separately (the reference calls
+    ``bn(x_b)`` sample by sample, :52-68): statistics over the P nodes of ONE graph.  Written as one autograd node with
+    the textbook backward -- six kernels forward, eleven backward, where the composed element-wise formula left autograd
+    some thirty small nodes per layer and iteration (the model-#3 step is bound by kernel launches, not by bytes).
+    Returns (out, mean [B,1,C], biased var [B,1,C]); the statistics carry no gradient (running-stat bookkeeping only)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        var, mean = torch.var_mean(x, dim=1, unbiased=False, keepdim=True)
+        rstd = torch.rsqrt(var + eps)
+        xhat = (x - mean) * rstd
+        ctx.save_for_backward(xhat, rstd, weight)
+        ctx.mark_non_differentiable(mean, var)
+        return torch.addcmul(bias, xhat, weight), mean, var
+
+    @staticmethod
+    def backward(ctx, g, _gmean, _gvar):
+        xhat, rstd, weight = ctx.saved_tensors
+        gxhat = g * weight
+        gw = (g * xhat).sum(dim=(0, 1)) if ctx.needs_input_grad[1] else None
+        gb = g.sum(dim=(0, 1)) if ctx.needs_input_grad[2] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            m1 = gxhat.mean(dim=1, keepdim=True)
+            m2 = (gxhat * xhat).mean(dim=1, keepdim=True)
+            gx = (gxhat - m1 - xhat * m2) * rstd
+        return gx, gw, gb, None
+
+
 class GNNHypernetwork3(nn.Module):
     def __init__(self, P, m, hidden_dim):
         super().__init__()
@@ -95,16 +125,16 @@ class GNNHypernetwork3(nn.Module):
             return F.batch_norm(x.transpose(1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0,
                                 bn.eps).transpose(1, 2)
         Bn, Pn, _ = x.shape
-        mean = x.mean(dim=1, keepdim=True)
-        var = x.var(dim=1, unbiased=False, keepdim=True)
-        out = (x - mean) / torch.sqrt(var + bn.eps) * bn.weight + bn.bias
+        out, mean, var = _PerSampleBatchNorm.apply(x, bn.weight, bn.bias, bn.eps)
         if bn.track_running_stats:
             with torch.no_grad():
                 mom = 0.1 if bn.momentum is None else bn.momentum
                 w = _ema_weights(Bn, mom, x.device, x.dtype)            # [1,B] weights of the B sequential updates (cached)
                 keep = (1.0 - mom) ** Bn
-                bn.running_mean.mul_(keep).add_((w @ mean[:, 0])[0])
-                bn.running_var.mul_(keep).add_((w @ var[:, 0])[0], alpha=Pn / max(Pn - 1, 1))
+                # running <- keep * running + sum_b w_b stat_b, one addmm each (the running variance is the unbiased one)
+                bn.running_mean.copy_(torch.addmm(bn.running_mean.unsqueeze(0), w, mean[:, 0], beta=keep)[0])
+                bn.running_var.copy_(torch.addmm(bn.running_var.unsqueeze(0), w, var[:, 0], beta=keep,
+                                                 alpha=Pn / max(Pn - 1, 1))[0])
                 bn.num_batches_tracked += Bn
         return out
 
@@ -168,19 +198,27 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
 
     def hyperparameters(self, AtAy, Atb, graph_list, adj_hat=None):
         """Hypernetwork on cat([AtAy, Atb]) -> (alpha, tau, rho, eta), each [B, P|1, 1, 1]  (reference :165-196)."""
+        return self._hyper_packed(AtAy, Atb, graph_list, adj_hat).unbind(dim=1)
+
+    def _hyper_packed(self, AtAy, Atb, graph_list, adj_hat=None):
         B = AtAy.shape[0]
         h = torch.cat([AtAy, Atb], dim=2)
         h = self.fc(self.decoder(self.encoder(h, graph_list, adj_hat)))
+        return self._scaled(h, B)
+
+    def _scaled(self, h, B):
+        """fc output [B, 4*(P|1)] -> [B, 4, P|1, 1, 1] = (alpha, tau, rho, eta): sigmoid, clamp, times the four maxima, tau /
+        rho / eta capped at 0.9999 (reference :170-196).  The four maxima are 0-dim CPU tensors (reference attributes); the
+        per-channel scale and cap live in two cached device vectors, so the four multiplies and three clamps of the
+        reference are one multiply and one clamp with the same fp32 rounding and the same (closed-interval) gradient mask."""
         h = torch.clamp(torch.sigmoid(h), min=1e-4, max=0.9999)
         h = h.view(B, 4, 1 if self.DADMM_mode == 'same' else self.P, 1, 1)
-        # the four maxima are 0-dim CPU tensors (reference attributes): as Python scalars they multiply with the same
-        # fp32 rounding and cost no host->device copy per iteration
-        am, tm, rm, em = (float(t) for t in (self.alpha_max, self.tau_max, self.rho_max, self.eta_max))
-        alpha = h[:, 0] * am
-        tau = torch.clamp(h[:, 1] * tm, max=0.9999)
-        rho = torch.clamp(h[:, 2] * rm, max=0.9999)
-        eta = torch.clamp(h[:, 3] * em, max=0.9999)
-        return alpha, tau, rho, eta
+        key = (str(h.device), h.dtype) + tuple(float(t) for t in (self.alpha_max, self.tau_max, self.rho_max, self.eta_max))
+        if getattr(self, "_scale_key", None) != key:
+            self._scale_vec = torch.tensor(key[2:], dtype=h.dtype, device=h.device).view(1, 4, 1, 1, 1)
+            self._cap_vec = torch.tensor([float("inf"), 0.9999, 0.9999, 0.9999], dtype=h.dtype, device=h.device).view(1, 4, 1, 1, 1)
+            self._scale_key = key
+        return torch.clamp(h * self._scale_vec, max=self._cap_vec)
 
     def forward(self, b, graph_list, training_iterations=None):
         """b [B,P,m,1] -> (Y [K,B,P,n,1], (alpha_k, tau_k, rho_k, eta_k) of the last iteration)."""
@@ -208,6 +246,7 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         Atb3 = Atb.squeeze(-1)
         clamps = DF.clamps_model3()
         Y, hyp = [], None
+        packed_path = type(self).hyperparameters is DLASSO_GNNHyp3_Progressive.hyperparameters
         for k in range(K):
             if guarded:
                 if bad(y):
@@ -217,8 +256,14 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
                     print(f"Warning: NaN/Inf detected in U_k at iteration {k}, resetting...")
                     U = torch.zeros_like(U)
             AtAy = DF.Contract.apply(y, W, Wt, self.contract_algo)            # [B,P,n]
-            hyp = self.hyperparameters(AtAy.unsqueeze(-1), Atb, graph_list, adj_hat)
-            hyp_s = torch.stack([h.reshape(len(y), -1).expand(len(y), self.P) for h in hyp], dim=1).contiguous()
+            if packed_path:
+                # the four outputs are views of one [B,4,P|1,1,1] tensor, which is also the step kernel's [B,4,P] layout
+                packed = self._hyper_packed(AtAy.unsqueeze(-1), Atb, graph_list, adj_hat)
+                hyp = packed.unbind(dim=1)
+                hyp_s = packed.reshape(len(y), 4, -1).expand(len(y), 4, self.P).contiguous()
+            else:                       # ``hyperparameters`` overridden by a subclass: honour it
+                hyp = self.hyperparameters(AtAy.unsqueeze(-1), Atb, graph_list, adj_hat)
+                hyp_s = torch.stack([h.reshape(len(y), -1).expand(len(y), self.P) for h in hyp], dim=1).contiguous()
             flag = torch.zeros(1, dtype=torch.int32, device=y.device) if guarded else (flags[k:k + 1] if flags is not None else None)
             y_n, U_n, d_n = DF.Step.apply(y, U, d, AtAy, Atb3, hyp_s, graph, clamps, flag)
             if guarded:

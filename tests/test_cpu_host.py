@@ -314,3 +314,51 @@ def test_hyper_parameter_table_backward_closed_form_matches_autograd():
         assert float((g_closed - sh.param.grad).abs().max()) < 1e-14
         if K < shape[0]:
             assert float(g_closed[K:].abs().max()) == 0.0
+
+
+def test_per_sample_batchnorm_function_matches_composed_formula_and_gradcheck():
+    """_PerSampleBatchNorm (one autograd node, textbook backward) against the composed element-wise formula it replaces
+    and against numerical differentiation, fp64."""
+    import gnn_dlasso_models_progressive as M
+    torch.manual_seed(3)
+    B, P, Cn, eps = 4, 6, 5, 1e-5
+    x = torch.randn(B, P, Cn, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cn, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(Cn, dtype=torch.float64, requires_grad=True)
+    out, mean, var = M._PerSampleBatchNorm.apply(x, w, b, eps)
+    mean_r = x.mean(dim=1, keepdim=True)
+    var_r = x.var(dim=1, unbiased=False, keepdim=True)
+    ref = (x - mean_r) / torch.sqrt(var_r + eps) * w + b
+    assert torch.allclose(out, ref, atol=1e-12) and torch.allclose(mean, mean_r, atol=1e-14) and torch.allclose(var, var_r, atol=1e-14)
+    assert not mean.requires_grad and not var.requires_grad
+    g = torch.randn_like(out)
+    got = torch.autograd.grad(out, (x, w, b), g, retain_graph=True)
+    want = torch.autograd.grad(ref, (x, w, b), g)
+    for a, r in zip(got, want):
+        assert torch.allclose(a, r, atol=1e-10), float((a - r).abs().max())
+    assert torch.autograd.gradcheck(lambda *a: M._PerSampleBatchNorm.apply(*a, eps)[0], (x, w, b), eps=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["diff", "same"])
+def test_model3_packed_hyperparameter_scaling_equals_reference_formula(mode):
+    """One multiply + one clamp over the packed [B,4,P|1,1,1] tensor == the reference's four multiplies and three clamps
+    (gnn_dlasso_models_progressive.py:170-196), values bit for bit and gradients."""
+    import gnn_dlasso_models_progressive as M
+    P, n, m, B = 4, 6, 3, 7
+    args = _args(P=P, n=n, m=m, K=2, GHyp_hidden=4)
+    args.DADMM_mode = mode
+    torch.manual_seed(11)
+    model = M.DLASSO_GNNHyp3_Progressive(torch.randn(1, P, m, n), args)
+    raw = (torch.randn(B, 4 * (P if mode == "diff" else 1)) * 6).requires_grad_(True)      # sigmoid saturates on some entries
+    packed = model._scaled(raw, B)
+    assert packed.shape == (B, 4, P if mode == "diff" else 1, 1, 1)
+    h = torch.clamp(torch.sigmoid(raw), min=1e-4, max=0.9999).view(B, 4, -1, 1, 1)
+    am, tm, rm, em = (float(t) for t in (model.alpha_max, model.tau_max, model.rho_max, model.eta_max))
+    ref = (h[:, 0] * am, torch.clamp(h[:, 1] * tm, max=0.9999), torch.clamp(h[:, 2] * rm, max=0.9999),
+           torch.clamp(h[:, 3] * em, max=0.9999))
+    for a, r in zip(packed.unbind(dim=1), ref):
+        assert torch.equal(a, r)
+    wts = torch.randn(B, 4, packed.shape[2], 1, 1)
+    g1, = torch.autograd.grad((packed * wts).sum(), raw, retain_graph=True)
+    g2, = torch.autograd.grad(sum((r * wts[:, i]).sum() for i, r in enumerate(ref)), raw)
+    assert torch.allclose(g1, g2, atol=1e-7)
