@@ -110,6 +110,7 @@ class HostGraph:
         per_graph = lambda c: int(c.reshape(G, P).sum(axis=1).max()) if G and P else 0
         self.max_events, self.max_adj = per_graph(ev_cnt), per_graph(adj_cnt)
         self.unique_graphs = uniq
+        self.nb_cnt, self.nb_flat = cnt, flat          # neighbour lists as read (normalized_adjacency)
 
 
 class _DeviceCSR:
@@ -144,6 +145,25 @@ class _DeviceCSR:
         else:
             self.max_events = self.max_adj = 0
         self.unique_graphs = uniq
+        self.nb_cnt, self.nb_flat = cnt_h, flat_h
+
+
+def normalized_adjacency_np(cnt, flat, n_graphs: int, P: int):
+    """A_hat [G,P,P] = D^-1/2 (Adj + I) D^-1/2 in float64 for all distinct graphs at once, from their neighbour lists
+    (``_extract``: cnt[G*P] list lengths, flat = neighbour ids).  Same arithmetic, element by element, as the per-graph
+    construction it replaces (identity first, off-diagonal ones, column sums ** -0.5, row scale then column scale) --
+    1024 fresh 5-node graphs took 85 ms per forward pass that way, more than the whole model-#3 training step."""
+    a = np.zeros((n_graphs, P, P), np.float64)
+    if n_graphs and P:
+        node = np.repeat(np.arange(n_graphs * P, dtype=np.int64), cnt)
+        g, u, v = node // P, node % P, np.asarray(flat, np.int64)
+        off = u != v
+        a[g[off], u[off], v[off]] = 1.0
+        a[g[off], v[off], u[off]] = 1.0
+        idx = np.arange(P)
+        a[:, idx, idx] = 1.0
+    d = a.sum(axis=1) ** -0.5
+    return d[:, :, None] * a * d[:, None, :]
 
 
 class BatchGraph:
@@ -159,6 +179,8 @@ class BatchGraph:
         self.n_graphs, self.P, self.B = host.n_graphs, host.P, (host.B if B is None else B)
         self.max_events, self.max_adj = host.max_events, host.max_adj
         self._keepalive = keepalive
+        self._nb = (getattr(host, "nb_cnt", None), getattr(host, "nb_flat", None))
+        self._adj_hat = {}
         self.c = _lib.Graph(self.n_graphs, self.P, self.ev_ptr.data_ptr(), self.ev_idx.data_ptr(), self.deg.data_ptr(),
                             self.graph_id.data_ptr() if self.graph_id is not None else None,
                             self.adj_ptr.data_ptr(), self.adj_idx.data_ptr(), self.max_events, self.max_adj)
@@ -173,6 +195,19 @@ class BatchGraph:
 
     def __len__(self):
         return self.B
+
+    def normalized_adjacency(self, dtype=torch.float32) -> torch.Tensor:
+        """[B,P,P] GCN propagation matrices of the batch's problems (``normalized_adjacency_np`` per distinct graph,
+        gathered by ``graph_id``), on this graph's device; built once per BatchGraph and dtype."""
+        hit = self._adj_hat.get(dtype)
+        if hit is None:
+            cnt, flat = self._nb
+            if cnt is None:
+                raise ValueError("this BatchGraph carries no neighbour lists")
+            m = torch.from_numpy(normalized_adjacency_np(cnt, flat, self.n_graphs, self.P)).to(device=self.device, dtype=dtype)
+            hit = m.index_select(0, self.graph_id.long()) if self.graph_id is not None else m.expand(self.B, self.P, self.P)
+            self._adj_hat[dtype] = hit
+        return hit
 
     @classmethod
     def from_graph_list(cls, graph_list, P: int, device) -> "BatchGraph":
@@ -201,6 +236,7 @@ class BatchGraph:
         out.__dict__.update(self.__dict__)
         out.graph_id = self.graph_id[lo:hi].contiguous() if self.graph_id is not None else None
         out.B = hi - lo
+        out._adj_hat = {}
         out.c = _lib.Graph(self.n_graphs, self.P, self.ev_ptr.data_ptr(), self.ev_idx.data_ptr(), self.deg.data_ptr(),
                            out.graph_id.data_ptr() if out.graph_id is not None else None,
                            self.adj_ptr.data_ptr(), self.adj_idx.data_ptr(), self.max_events, self.max_adj)

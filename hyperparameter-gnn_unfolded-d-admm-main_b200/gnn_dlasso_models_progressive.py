@@ -38,23 +38,14 @@ class GCNConv(nn.Module):
 
 
 def normalized_adjacency(graph_list, P, device, dtype=torch.float32):
-    """A_hat [B,P,P] = D^-1/2 (Adj + I) D^-1/2 per sample, built once per distinct graph object."""
-    uniq, index, gid = [], {}, []
-    for g in graph_list:
-        if id(g) not in index:
-            index[id(g)] = len(uniq)
-            uniq.append(g)
-        gid.append(index[id(g)])
-    mats = np.zeros((len(uniq), P, P), np.float64)
-    for i, g in enumerate(uniq):
-        a = np.eye(P)
-        for u, v in g.edges():
-            if u != v:
-                a[u, v] = a[v, u] = 1.0
-        d = a.sum(axis=0) ** -0.5
-        mats[i] = d[:, None] * a * d[None, :]
-    m = torch.from_numpy(mats).to(device=device, dtype=dtype)
-    return m[torch.as_tensor(gid, device=device)] if len(uniq) > 1 else m.expand(len(graph_list), P, P)
+    """A_hat [B,P,P] = D^-1/2 (Adj + I) D^-1/2 per sample, built once per distinct graph object (vectorised over the
+    graphs: ``dadmm_b200.graph.normalized_adjacency_np``); ``graph_list`` may be a prebuilt ``BatchGraph``."""
+    from dadmm_b200 import graph as G
+    if isinstance(graph_list, BatchGraph):
+        return graph_list.normalized_adjacency(dtype).to(device)
+    uniq, gid, cnt, flat = G._extract(graph_list, P)
+    m = torch.from_numpy(G.normalized_adjacency_np(cnt, flat, len(uniq), P)).to(device=device, dtype=dtype)
+    return m.index_select(0, torch.as_tensor(gid, device=device).long()) if len(uniq) > 1 else m.expand(len(graph_list), P, P)
 
 
 _EMA_CACHE = {}
@@ -230,7 +221,7 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         A, W, Wt, At = self._operators(device)
         Atb = DF.contract(At, b.to(W.dtype).squeeze(-1), algo=self.contract_algo).unsqueeze(-1)   # [B,P,n,1]
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
-        adj_hat = normalized_adjacency(graph_list, self.P, device, W.dtype)
+        adj_hat = graph.normalized_adjacency(W.dtype)                 # cached on the BatchGraph (itself cached per graph_list)
         y0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
         U0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
         d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2

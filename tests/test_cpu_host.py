@@ -362,3 +362,36 @@ def test_model3_packed_hyperparameter_scaling_equals_reference_formula(mode):
     g1, = torch.autograd.grad((packed * wts).sum(), raw, retain_graph=True)
     g2, = torch.autograd.grad(sum((r * wts[:, i]).sum() for i, r in enumerate(ref)), raw)
     assert torch.allclose(g1, g2, atol=1e-7)
+
+
+def test_vectorised_normalized_adjacency_equals_per_graph_construction():
+    """GCN propagation matrices D^-1/2 (Adj + I) D^-1/2 (gnn_dlasso_models_progressive.py:43 via PyG's gcn_norm): the
+    all-graphs-at-once construction (module function and the BatchGraph-cached form the forward uses) against the
+    per-graph loop it replaces, bit for bit -- self-loops, isolated nodes, repeated graph objects, one shared graph."""
+    import networkx as nx
+    import gnn_dlasso_models_progressive as M
+    from dadmm_b200.graph import BatchGraph
+
+    def per_graph(graph_list, P):
+        out = []
+        for g in graph_list:
+            a = np.eye(P)
+            for u, v in g.edges():
+                if u != v:
+                    a[u, v] = a[v, u] = 1.0
+            d = a.sum(axis=0) ** -0.5
+            out.append(d[:, None] * a * d[None, :])
+        return torch.from_numpy(np.stack(out)).float()
+
+    P = 9
+    gs = _ingestion_graphs(P)
+    want = per_graph(gs, P)
+    assert torch.equal(M.normalized_adjacency(gs, P, "cpu"), want)
+    bg = BatchGraph.from_graph_list(gs, P, "cpu")
+    got = bg.normalized_adjacency(torch.float32)
+    assert torch.equal(got, want) and bg.normalized_adjacency(torch.float32) is got          # cached
+    assert torch.equal(M.normalized_adjacency(bg, P, "cpu"), want)
+    assert torch.equal(bg.shard(3, 9).normalized_adjacency(), want[3:9])
+    one = [gs[2]] * 5
+    assert torch.equal(BatchGraph.from_graph_list(one, P, "cpu").normalized_adjacency(), per_graph(one, P))
+    assert torch.equal(M.normalized_adjacency(one, P, "cpu"), per_graph(one, P))
