@@ -227,8 +227,11 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
         flags = torch.zeros(max(K, 1), dtype=torch.int32, device=device) if self.check_finite else None
         out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, flags, guarded=False)
-        if flags is not None and bool(flags.any()):
-            out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, None, guarded=True)
+        if flags is not None:
+            if bool(flags.any()):
+                out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, None, guarded=True)
+            else:
+                out[0]._dadmm_finite = out[0]._version      # no kernel saw a non-finite value (compute_loss skips its scan)
         return out
 
     def _iterate(self, K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, flags, guarded):

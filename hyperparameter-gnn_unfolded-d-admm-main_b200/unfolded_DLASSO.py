@@ -162,6 +162,8 @@ class DLASSO_unfolded(nn.Module):
                 Atb = self._atb(self._operators(W.device)[3], b, W.dtype)
             return self._run_guarded(hyp, W, Wt, Atb, y0, U0, d0, graph, K)
         Y._dadmm_handle = handle
+        if flags is not None:
+            Y._dadmm_finite = Y._version      # no kernel saw a non-finite value => Y is finite (compute_loss skips its scan)
         return Y
 
     def _run_guarded(self, hyp, W, Wt, Atb, y0, U0, d0, graph, K):
