@@ -395,3 +395,40 @@ def test_vectorised_normalized_adjacency_equals_per_graph_construction():
     one = [gs[2]] * 5
     assert torch.equal(BatchGraph.from_graph_list(one, P, "cpu").normalized_adjacency(), per_graph(one, P))
     assert torch.equal(M.normalized_adjacency(one, P, "cpu"), per_graph(one, P))
+
+
+def test_abi_v5_host_side_contracts_without_a_gpu():
+    """Pieces of ABI v5 that are decided on the host: the PDL switch, operator-split sizes per route, the reverse
+    sweep's partial-sum workspace, and the rule for omitting Atb."""
+    import ctypes as C
+    from dadmm_b200 import _lib
+    lib = _lib.lib
+    prev = _lib.set_pdl(False)
+    assert _lib.set_pdl(True) is False and _lib.set_pdl(prev) is True
+    # operator split: nothing off the fused tensor-core path; W alone on the single-stage route; F1 + F2 on the two-stage one
+    B, P, n, m = 256, 3, 512, 160
+    split = lambda rows, k: 256 + (rows * ((k + 7) // 8 * 8) * 4 + 255) // 256 * 256          # f16::split_bytes
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F64, _lib.ALGO_AUTO, B, P, n, m) == 0
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F32, _lib.ALGO_SIMT, B, P, n, m) == 0
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F32, _lib.ALGO_AUTO, 8, P, n, m) == 0            # batch below a tile
+    assert lib.dadmm_unfolded_uses_factor(_lib.F32, _lib.ALGO_AUTO, B, P, n, m) == 1
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F32, _lib.ALGO_AUTO, B, P, n, m) == split(P * m, n) + split(P * n, m)
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F32, _lib.ALGO_AUTO, B, P, n, 0) == split(P * n, n)
+    assert lib.dadmm_unfolded_op_split_bytes(_lib.F32, _lib.ALGO_AUTO, B, P, n, 256) == split(P * n, n)   # 8m > 3n: single stage
+    # reverse sweep: K levels of [csplit][B][P][4] partial rows fit the workspace
+    K = 6
+    fwd, bwd = (lib.dadmm_unfolded_ws_bytes(_lib.F32, _lib.ALGO_SIMT, B, P, n, K, back, 0) for back in (0, 1))
+    assert bwd >= 3 * B * P * n * 4 + K * B * P * 4 * 4 and fwd % 256 == 0 and bwd % 256 == 0
+    # Atb may be omitted only on the two-stage route with the observation term in the factor
+    clamps = (_lib.Clamps * K)()
+    one = C.c_void_p(256)                                  # never dereferenced: validation fails first
+    g = _lib.Graph(1, P, 256, 256, 256, None, 256, 256, 0, 0)
+
+    def fwd_rc(atb, fac):
+        return lib.dadmm_unfolded_fwd(_lib.F32, _lib.ALGO_AUTO, B, P, n, K, C.byref(g), clamps, one, one,
+                                      C.byref(fac) if fac else None, atb, one, one, one, one, None, None, one, 0, None, None, None, None)
+    assert fwd_rc(None, None) < 0 and b"Atb is required" in lib.dadmm_last_error()
+    assert fwd_rc(None, _lib.Factor(m, 256, 256, None)) < 0 and b"Atb is required" in lib.dadmm_last_error()
+    assert fwd_rc(None, _lib.Factor(256, 256, 256, 256)) < 0 and b"Atb is required" in lib.dadmm_last_error()   # not two-stage
+    rc = fwd_rc(None, _lib.Factor(m, 256, 256, 256))      # allowed: the next check (workspace size 0) is the one that fires
+    assert rc < 0 and b"workspace too small" in lib.dadmm_last_error()
