@@ -171,8 +171,33 @@ def case_model3(name, P, n, m, K, B, hidden, seed=3):
     print(f"{name}: Y{tuple(Y.shape)} loss_final={float(lf.detach()):.8f} -> {os.path.getsize(path)/1e3:.0f} KB")
 
 
+def sparse_bridged_er(P, prob, seed):
+    """bench.py's config-4 graph recipe: ER at the stated probability (no 0.3 floor), components bridged as in
+    gnn_dlasso_progressive.py:186-190 -- sparse graphs with leaves, bridges and long neighbour-order permutations."""
+    g = nx.erdos_renyi_graph(P, prob, seed=seed)
+    if not nx.is_connected(g):
+        comps = list(nx.connected_components(g))
+        for i in range(len(comps) - 1):
+            g.add_edge(list(comps[i])[0], list(comps[i + 1])[0])
+    return g
+
+
+def extra_cases():
+    """Fixtures used by the CPU oracle tests only (tests/helpers.py: MODEL1_EXTRA_CASES)."""
+    # 6. config-4-like structure in miniature: many agents, sparse bridged per-problem graphs, train-mode table with
+    #    random entries (some rows above the 0.8 penalty threshold), m = n/4
+    P, n, m, K, B = 12, 40, 10, 10, 6
+    graphs = [sparse_bridged_er(P, 0.12, seed=300 + i) for i in range(B)]
+    torch.manual_seed(6)
+    case_model1("m1_cfg4like_P12_n40", P=P, n=n, m=m, K=K, B=B, mode="diff", graphs=graphs,
+                param=torch.randn(K, P, 4) * 0.3 + 0.2, training=True, a_scale=0.1)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--extra-only" in sys.argv:
+        extra_cases()
+        return
     # 1. untrained (zero-init) table, default set_A conditioning (chaotic regime), one shared ER graph
     g = nx.erdos_renyi_graph(5, 0.5, seed=1)
     case_model1("m1_zero_P5_n64", P=5, n=64, m=16, K=8, B=4, mode="diff", graphs=[g] * 4,
@@ -199,6 +224,7 @@ def main():
                 param=sd["seq_hyp.param"].clone(), training=False, alpha_max=0.06, a_scale=0.1)
     # 5. model #3 recurrence with frozen hypernetwork outputs
     case_model3("m3_frozen_P5_n32", P=5, n=32, m=8, K=4, B=3, hidden=8)
+    extra_cases()
 
 
 if __name__ == "__main__":

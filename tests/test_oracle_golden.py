@@ -5,7 +5,7 @@ import math
 import pytest
 import torch
 
-from helpers import MODEL1_CASES, MODEL3_CASES, Golden, rel_l2
+from helpers import MODEL1_CASES, MODEL1_EXTRA_CASES, MODEL3_CASES, Golden, rel_l2
 from oracle import dadmm_oracle as O
 
 
@@ -17,7 +17,7 @@ def _hyp_for(g, dtype=torch.float32):
     return hyp
 
 
-@pytest.mark.parametrize("name", MODEL1_CASES)
+@pytest.mark.parametrize("name", MODEL1_CASES + MODEL1_EXTRA_CASES)
 def test_model1_forward_bit_exact(name):
     """Loop-order oracle == reference forward, bit for bit, in fp32."""
     g = Golden(name)
@@ -32,7 +32,7 @@ def test_model1_forward_bit_exact(name):
     assert torch.allclose(_hyp_for(g)[-1].unsqueeze(-1)[: g.t("hyp_last").shape[0]], g.t("hyp_last"), rtol=0, atol=0)
 
 
-@pytest.mark.parametrize("name", MODEL1_CASES)
+@pytest.mark.parametrize("name", MODEL1_CASES + MODEL1_EXTRA_CASES)
 def test_model1_fp64_forward_and_grad(name):
     """Vectorised (dense 2L) oracle in fp64 vs the reference run in fp64: proves the algebra,
     including d loss_final / d param through all K iterations."""
@@ -52,7 +52,7 @@ def test_model1_fp64_forward_and_grad(name):
     assert rel_l2(param.grad, g.t("dparam64")) < 1e-7
 
 
-@pytest.mark.parametrize("name", MODEL1_CASES)
+@pytest.mark.parametrize("name", MODEL1_CASES + MODEL1_EXTRA_CASES)
 def test_model1_fp32_grad_noise_floor(name):
     """fp32 oracle gradient vs reference fp32 gradient: same order of error as the reference's
     own fp32-vs-fp64 gap (SURVEY.md 8c protocol)."""
