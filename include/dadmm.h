@@ -22,7 +22,8 @@
  * (DADMM_F32 / DADMM_F64) unless a stride is given; state tensors are [B,P,n] with n fastest
  * (the reference's [B,P,n,1]); the caller owns every buffer (workspaces included: nothing is
  * allocated here); calls are asynchronous on `stream` (a cudaStream_t); no global mutable
- * state apart from the thread-local error string.  Return value: 0 success, <0 invalid
+ * state apart from the thread-local error string, the launch counter / profiling switch and
+ * the programmatic-launch switch (dadmm_set_pdl).  Return value: 0 success, <0 invalid
  * argument, >0 a cudaError_t.  Nothing throws.
  */
 #ifndef DADMM_H_
