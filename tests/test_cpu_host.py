@@ -432,3 +432,46 @@ def test_abi_v5_host_side_contracts_without_a_gpu():
     assert fwd_rc(None, _lib.Factor(256, 256, 256, 256)) < 0 and b"Atb is required" in lib.dadmm_last_error()   # not two-stage
     rc = fwd_rc(None, _lib.Factor(m, 256, 256, 256))      # allowed: the next check (workspace size 0) is the one that fires
     assert rc < 0 and b"workspace too small" in lib.dadmm_last_error()
+
+
+def test_graph_ingestion_property_random_insertion_orders():
+    """Property test (hypothesis): for random multigraph-free edge lists in random insertion order -- self-loops, isolated
+    nodes and duplicates included -- the vectorised CSR equals the per-graph event lists of unfolded_DLASSO.py:132-139,
+    degrees equal ``len(list(g.neighbors(p)))``, and delta = 2 L y computed from the event lists equals the reference's
+    double loop."""
+    import networkx as nx
+    from hypothesis import given, settings, strategies as st
+    from dadmm_b200 import graph as G
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 9).flatmap(lambda P: st.tuples(st.just(P), st.lists(st.lists(
+        st.tuples(st.integers(0, P - 1), st.integers(0, P - 1)), max_size=14), min_size=1, max_size=4))))
+    def check(case):
+        P, edge_lists = case
+        gs = []
+        for edges in edge_lists:
+            g = nx.Graph()
+            g.add_nodes_from(range(P))
+            g.add_edges_from(edges)
+            gs.append(g)
+        h = G.HostGraph(gs, P)
+        rng = np.random.default_rng(P)
+        y = rng.standard_normal((len(gs), P, 3))
+        for gi, g in enumerate(gs):
+            ev = G.event_lists(g, P)
+            delta = np.zeros((P, 3))
+            for p in range(P):                       # the reference's accumulation, unfolded_DLASSO.py:132-139
+                for j in g.neighbors(p):
+                    diff = y[gi, p] - y[gi, j]
+                    delta[p] += diff
+                    delta[j] -= diff
+            for p in range(P):
+                q = gi * P + p
+                lst = h.ev_idx[h.ev_ptr[q]:h.ev_ptr[q + 1]].tolist()
+                assert lst == ev[p]
+                assert h.deg[q] == len(list(g.neighbors(p)))
+                acc = np.zeros(3)
+                for e in lst:                        # what the forward level kernel does with the event list
+                    acc = acc + (y[gi, p] - y[gi, e])
+                assert np.array_equal(acc, delta[p])
+    check()
