@@ -90,3 +90,80 @@ def test_delta_is_twice_laplacian():
     assert rel_l2(d1, d2) < 1e-6
     deg = O.degrees(g.graphs, g.P)
     assert torch.equal(O.laplacian2(g.graphs, g.P).diagonal(dim1=1, dim2=2), 2 * deg[:, :, 0, 0])
+
+
+@pytest.mark.ref
+def test_oracle_equals_reference_on_random_configurations():
+    """Beyond the committed fixtures: 24 seeded random configurations (agents, sizes, K, 'same'/'diff' tables, train /
+    eval mode, shared / per-problem graphs with and without bridging, conditioning of A) run through the UNMODIFIED
+    reference class here and through the oracle -- forward bit for bit in fp32, loss to 1e-6, d loss / d param in fp64
+    to 1e-7.  (Skipped where the reference checkout is absent.)"""
+    import argparse
+    import random
+    import networkx as nx
+    from oracle import ref_harness
+    ref = ref_harness.load("unfolded_DLASSO")
+    utils = ref_harness.load("gnn_dlasso_utils")
+    rnd = random.Random(2024)
+    for case in range(24):
+        P, n = rnd.randint(2, 9), rnd.randint(3, 40)
+        m, K, B = rnd.randint(1, max(1, n // 2)), rnd.randint(1, 9), rnd.randint(1, 4)
+        mode, training = rnd.choice(["diff", "same"]), rnd.choice([True, False])
+        args = argparse.Namespace(m=m, n=n, P=P, GHN_iter_num=K, DADMM_mode=mode, alpha_max=rnd.choice([0.05, 0.1]), tau_max=0.99,
+                                  rho_max=0.99, eta_max=0.99, max_penalty_threshold=0.8, penalty_reduction_factor=0.95,
+                                  batch_size=B, snr=4)
+        torch.manual_seed(case)
+        A = utils.set_A(args) * rnd.choice([1.0, 0.1])
+        label = 2 * torch.randn(B, n, 1) * (torch.rand(B, n, 1) <= 0.25)
+        b = torch.stack([A[0, p] @ label for p in range(P)], dim=1)
+        if rnd.random() < 0.4:
+            graphs = [nx.erdos_renyi_graph(P, 0.5, seed=case)] * B
+        else:
+            graphs = []
+            for i in range(B):
+                g = nx.erdos_renyi_graph(P, rnd.choice([0.15, 0.5, 0.9]), seed=100 * case + i)
+                if rnd.random() < 0.5 and not nx.is_connected(g):
+                    comps = list(nx.connected_components(g))
+                    for c in range(len(comps) - 1):
+                        g.add_edge(list(comps[c])[0], list(comps[c + 1])[0])
+                graphs.append(g)
+        param = torch.randn(K, 1 if mode == "same" else P, 4) * 0.5 + 0.3
+        mp = torch.tensor([args.alpha_max, 0.99, 0.99, 0.99])
+        outs = {}
+        for dt in (torch.float32, torch.float64):
+            with ref_harness.default_dtype(dt):
+                model = ref.DLASSO_unfolded(A.to(dt), args)
+                model.train(training)
+                with torch.no_grad():
+                    model.seq_hyp.param.copy_(param.to(dt))
+                torch.manual_seed(1000 + case)
+                Y, _ = model(b.to(dt), graphs)
+                lm, lf = utils.compute_loss(Y, label.to(dt))
+                lf.backward()
+                outs[dt] = (Y.detach(), float(lm.detach()), float(lf.detach()), model.seq_hyp.param.grad.detach().clone())
+        torch.manual_seed(1000 + case)
+        noise = [torch.randn((B, P, n, 1)) for _ in range(3)]
+        # fp32, the reference's accumulation order: bit for bit
+        hyp = O.hyp_table(param, mp, training)
+        hyp = hyp.expand(-1, P, -1) if hyp.shape[1] == 1 else hyp
+        Yo = O.unfolded_forward(O.atx(A, A), O.atx(A, b), graphs, *(t * 1e-2 for t in noise), hyp, exact_delta=True)
+        assert torch.equal(Yo, outs[torch.float32][0]), (case, P, n, m, K, B, mode, training)
+        lm, lf = O.loss(Yo, label)
+        assert math.isclose(float(lm), outs[torch.float32][1], rel_tol=1e-6) and math.isclose(float(lf), outs[torch.float32][2], rel_tol=1e-6)
+        # fp64, differentiable form: algebra incl. the gradient through all K iterations
+        dt = torch.float64
+        with ref_harness.default_dtype(dt):  # the reference's own fp64 draw (a different stream from fp32's)
+            torch.manual_seed(1000 + case)
+            noise64 = [torch.randn((B, P, n, 1)) for _ in range(3)]
+        mp64 = torch.tensor([args.alpha_max, 0.99, 0.99, 0.99], dtype=dt)
+        p64 = param.to(dt).clone().requires_grad_(True)
+        hyp = O.hyp_table(p64, mp64, training)
+        hyp = hyp.expand(-1, P, -1) if hyp.shape[1] == 1 else hyp
+        A64 = A.to(dt)
+        Y64 = O.unfolded_forward(O.atx(A64, A64), O.atx(A64, b.to(dt)), graphs, *(t * 1e-2 for t in noise64), hyp)
+        _, lf64 = O.loss(Y64, label.to(dt))
+        lf64.backward()
+        assert rel_l2(Y64.detach(), outs[dt][0]) < 1e-9, case
+        ref_g = outs[dt][3]
+        if float(ref_g.abs().max()) > 0:
+            assert rel_l2(p64.grad, ref_g) < 1e-7, (case, rel_l2(p64.grad, ref_g))
