@@ -138,6 +138,14 @@ class ClockSampler:
 # GPU box; oracle/dadmm_oracle.py::reference_port_fwd_bwd keeps its cost model: per-agent matmul loops,
 # Python neighbour loops with in-place slice updates, autograd over all of it)
 # ---------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """The CPU legs are one process and take every host thread this process may run on (torchrun exports
+    OMP_NUM_THREADS=1 to its ranks, which would otherwise time the reference on one core)."""
+    host_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < host_threads:
+        torch.set_num_threads(host_threads)
+
+
 def cpu_baseline_sample(w, B_ref=None):
     from oracle import dadmm_oracle as O
     B_ref = B_ref or w["B_ref"]
@@ -177,6 +185,7 @@ def run_reference_arm(opt, w):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    use_all_host_threads()
     # size the per-step sample so that (warmup + steps) samples end within ~3 minutes: calibrate on 1 problem
     cal, _ = cpu_baseline_sample(w, 1)
     t1 = cal()
@@ -352,6 +361,7 @@ def run_ours(opt, w):
             "gpu_launches": launches, "loss_final": loss_val,
             "roofline": roofline, "kernel_breakdown_ms": breakdown}
     if opt.cpu_baseline and world == 1:       # rank 0 at N=1 only
+        use_all_host_threads()
         run, B_ref = cpu_baseline_sample(w)
         t = min(run() for _ in range(1 if w["P"] >= 50 else 2))
         line["cpu_baseline"] = {"value": w["K"] * B_ref / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
