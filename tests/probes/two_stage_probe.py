@@ -1,8 +1,12 @@
 """CPU probe: does a two-stage contraction A^T (A y) -- half the flops of AtA y at m = n/4 -- keep the K-step
-parity gate?  Variants are run through the oracle recurrence and compared with the reference's fp64 run."""
+parity gate?  Variants are run through the oracle recurrence and compared with the reference's fp64 run.
+
+TEST INFRASTRUCTURE (lives under tests/ because it executes the oracle); not collected by pytest, run by hand:
+    python tests/probes/two_stage_probe.py"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(TESTS))
+sys.path.insert(0, TESTS)
 import torch
 from helpers import Golden, rel_l2
 from oracle import dadmm_oracle as O
@@ -33,7 +37,7 @@ def run(name, g, contract_fn, grad=True):
     Y = []
     for k in range(g.K):
         h = table[k]
-        al, ta, rh, et = (h[:, i].reshape(1, g.P, 1, 1) for i in range(4))
+        al, ta, rh, et = (h[:, i].reshape(1, -1, 1, 1).expand(1, g.P, 1, 1) for i in range(4))   # 'same' tables have one row
         a = contract_fn(y)
         y, U, d, _ = O.step(a, Atb, deg, y, U, d, al, ta, rh, et, O.clamps_model1(k), lambda v: O.delta_dense(lap2, v))
         Y.append(y)
