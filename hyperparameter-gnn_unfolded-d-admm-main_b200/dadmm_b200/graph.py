@@ -6,6 +6,9 @@ of a batch (the drivers pass ``[graph]*B`` or B fresh graphs) is converted once 
 *event-ordered* neighbour list -- the neighbour ids in the exact order the reference accumulates
 ``y_q - y_e`` into ``delta[q]`` -- so the kernels reproduce ``delta = 2*L*y`` with the reference's
 rounding, and ``deg[p] = len(list(graph.neighbors(p)))``.
+
+``sample_erdos_renyi`` makes such a batch without ``networkx``: the driver's per-problem generation loop
+(gnn_dlasso_progressive.py:181-191) as tensor passes on the device.
 """
 from __future__ import annotations
 
@@ -119,9 +122,22 @@ class _DeviceCSR:
 
     def __init__(self, graph_list: Sequence, P: int, device):
         uniq, gid, cnt_h, flat_h = _extract(graph_list, P)
-        G, dev = len(uniq), torch.device(device)
-        cnt = torch.from_numpy(cnt_h).to(dev)
-        flat = torch.from_numpy(flat_h).to(dev)
+        dev = torch.device(device)
+        self._build(len(uniq), P, len(graph_list), gid, torch.from_numpy(cnt_h).to(dev), torch.from_numpy(flat_h).to(dev), dev)
+        self.unique_graphs = uniq
+        self.nb_cnt, self.nb_flat = cnt_h, flat_h
+
+    @classmethod
+    def from_lists(cls, G: int, P: int, cnt: torch.Tensor, flat: torch.Tensor) -> "_DeviceCSR":
+        """G distinct graphs, one per problem, from neighbour lists already on the device (``sample_erdos_renyi``):
+        cnt[G*P] list lengths, flat = neighbour ids in visit order (both int64)."""
+        self = object.__new__(cls)
+        self._build(G, P, G, np.arange(G, dtype=np.int32), cnt, flat, cnt.device)
+        self.unique_graphs = None
+        self.nb_cnt, self.nb_flat = cnt, flat          # read back lazily (BatchGraph.normalized_adjacency)
+        return self
+
+    def _build(self, G, P, B, gid, cnt, flat, dev):
         node = torch.repeat_interleave(torch.arange(G * P, device=dev), cnt)
         gbase = node - node % P
         dst = gbase + flat
@@ -138,14 +154,12 @@ class _DeviceCSR:
         self.adj_ptr, self.adj_idx = ptr(adj_cnt), arr(flat[keep])
         self.deg = cnt.to(torch.int32) if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph_id = gid if G > 1 else None
-        self.n_graphs, self.P, self.B = G, P, len(graph_list)
+        self.n_graphs, self.P, self.B = G, P, B
         if G and P:
             mx = torch.stack((ev_cnt.view(G, P).sum(1).max(), adj_cnt.view(G, P).sum(1).max())).tolist()   # one sync
             self.max_events, self.max_adj = int(mx[0]), int(mx[1])
         else:
             self.max_events = self.max_adj = 0
-        self.unique_graphs = uniq
-        self.nb_cnt, self.nb_flat = cnt_h, flat_h
 
 
 def normalized_adjacency_np(cnt, flat, n_graphs: int, P: int):
@@ -204,10 +218,55 @@ class BatchGraph:
             cnt, flat = self._nb
             if cnt is None:
                 raise ValueError("this BatchGraph carries no neighbour lists")
+            if isinstance(cnt, torch.Tensor):          # sampled on the device: one read-back, kept
+                cnt, flat = cnt.cpu().numpy(), flat.cpu().numpy()
+                self._nb = (cnt, flat)
             m = torch.from_numpy(normalized_adjacency_np(cnt, flat, self.n_graphs, self.P)).to(device=self.device, dtype=dtype)
             hit = m.index_select(0, self.graph_id.long()) if self.graph_id is not None else m.expand(self.B, self.P, self.P)
             self._adj_hat[dtype] = hit
         return hit
+
+    def to_networkx(self, problems=None) -> list:
+        """``networkx.Graph`` objects of the given problems (default: all), edges inserted so that every node's
+        ``neighbors()`` order equals the stored list order -- ``BatchGraph.from_graph_list`` of the result reproduces
+        this graph's arrays.  Needs the neighbour lists (any graph built by this module has them)."""
+        import networkx as nx
+        cnt, flat = self._nb
+        if cnt is None:
+            raise ValueError("this BatchGraph carries no neighbour lists")
+        if isinstance(cnt, torch.Tensor):
+            cnt, flat = cnt.cpu().numpy(), flat.cpu().numpy()
+            self._nb = (cnt, flat)
+        P = self.P
+        ptr = np.concatenate(([0], np.cumsum(cnt)))
+        gid = self.graph_id.cpu().numpy() if self.graph_id is not None else np.zeros(self.B, np.int64)
+        built, out = {}, []
+        for b in (range(self.B) if problems is None else problems):
+            g = int(gid[b])
+            if g not in built:
+                G = nx.Graph()
+                G.add_nodes_from(range(P))
+                rows = [flat[ptr[g * P + u]:ptr[g * P + u + 1]].tolist() for u in range(P)]
+                # insertion order that yields these lists: repeatedly take the earliest pending edge whose two ends
+                # both have it at the head of their remaining list (always exists for lists networkx could hold)
+                pos = [0] * P
+                remaining = sum(len(r) for r in rows)
+                while remaining:
+                    progressed = False
+                    for u in range(P):
+                        while pos[u] < len(rows[u]):
+                            v = rows[u][pos[u]]
+                            if v == u:
+                                G.add_edge(u, u); pos[u] += 1; remaining -= 1; progressed = True
+                            elif pos[v] < len(rows[v]) and rows[v][pos[v]] == u:
+                                G.add_edge(u, v); pos[u] += 1; pos[v] += 1; remaining -= 2; progressed = True
+                            else:
+                                break
+                    if not progressed:
+                        raise ValueError("neighbour lists are not the adjacency order of any undirected graph")
+                built[g] = G
+            out.append(built[g])
+        return out
 
     @classmethod
     def from_graph_list(cls, graph_list, P: int, device) -> "BatchGraph":
@@ -241,6 +300,67 @@ class BatchGraph:
                            out.graph_id.data_ptr() if out.graph_id is not None else None,
                            self.adj_ptr.data_ptr(), self.adj_idx.data_ptr(), self.max_events, self.max_adj)
         return out
+
+
+def _erdos_renyi_lists(B: int, P: int, p: float, device, generator=None, connect: bool = True):
+    """Neighbour lists of B independent G(P, p) graphs, drawn and (optionally) bridged with tensor passes on ``device``.
+
+    Returns (cnt[B*P] int64, flat int64, n_bridges[B] int64).  List order is the one ``networkx`` would hold had each
+    graph been built the way the reference's driver builds it (gnn_dlasso_progressive.py:181-191): the G(P, p) edges
+    inserted in (u, v), u < v, lexicographic order -- every node's neighbours ascending -- then one bridging edge
+    between consecutive connected components, appended after them."""
+    dev = torch.device(device)
+    idx = torch.arange(P, device=dev)
+    upper = idx.view(1, P, 1) < idx.view(1, 1, P)
+    er = (torch.rand((B, P, P), device=dev, generator=generator) < p) & upper
+    er = er | er.transpose(1, 2)                                           # [B,P,P] symmetric, no self-loops
+    bridge = torch.zeros_like(er)
+    n_bridges = torch.zeros(B, dtype=torch.int64, device=dev)
+    if connect and P > 1:
+        # connected components: propagate the smallest node id over the edges until nothing changes (a component's
+        # label is its smallest node -- the order nx.connected_components lists them in)
+        label = idx.expand(B, P).contiguous()
+        big = torch.full((), P, dtype=label.dtype, device=dev)
+        for _ in range(P):
+            nb_min = torch.where(er, label.unsqueeze(1), big).amin(dim=2)
+            new = torch.minimum(label, nb_min)
+            new = torch.gather(new, 1, new)                                # pointer jumping: label of my label
+            if torch.equal(new, label):
+                break
+            label = new
+        rep = label == idx                                                 # component representatives, ascending in p
+        # next representative after p (P when none): reverse running minimum of the representatives' ids
+        cand = torch.where(rep, idx, big).flip(1).cummin(dim=1).values.flip(1)            # min id of a rep at >= p
+        nxt = torch.cat((cand[:, 1:], big.expand(B, 1)), dim=1)                           # ... at > p
+        has = rep & (nxt < P)
+        b_i, u_i = has.nonzero(as_tuple=True)
+        v_i = nxt[b_i, u_i]
+        bridge[b_i, u_i, v_i] = True
+        bridge[b_i, v_i, u_i] = True
+        n_bridges = has.sum(dim=1)
+    both = torch.cat((er, bridge), dim=2)                                  # [B,P,2P]: per node, G(P,p) edges then bridges
+    cnt = both.sum(dim=2).reshape(-1)
+    flat = both.nonzero(as_tuple=True)[2] % P                              # row-major = (graph, node, list position)
+    return cnt, flat, n_bridges
+
+
+def sample_erdos_renyi(B: int, P: int, p: float, device, generator=None, connect: bool = True) -> "BatchGraph":
+    """A batch of B fresh G(P, p) graphs, made connected the way the reference's driver does it, as a ``BatchGraph``
+    -- sampling, component search, bridging and the CSR build all run as tensor passes on ``device``, so a batch of
+    4096 50-agent problems does not spend seconds in ``networkx`` before every step (3 s for the generation loop of
+    gnn_dlasso_progressive.py:181-191 on this container's CPU, against a 0.1 s training step).  Pass the result wherever
+    the modules take ``graph_list``.
+
+    Same distribution as the driver's loop, not the same random stream (``networkx`` draws from Python's ``random``);
+    one documented difference in the bridging: the driver joins ``list(component)[0]`` of consecutive components --
+    whichever element the Python set happens to yield first -- this joins their smallest nodes.
+    ``BatchGraph.to_networkx`` rebuilds the ``networkx`` objects (same insertion order) when something else needs them."""
+    if not (0.0 <= p <= 1.0) or B < 1 or P < 1:
+        raise ValueError("sample_erdos_renyi: need B >= 1, P >= 1, 0 <= p <= 1")
+    cnt, flat, n_bridges = _erdos_renyi_lists(B, P, p, device, generator, connect)
+    bg = BatchGraph(_DeviceCSR.from_lists(B, P, cnt, flat), device)
+    bg.n_bridges = n_bridges
+    return bg
 
 
 _CACHE_MAX = 8

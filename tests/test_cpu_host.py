@@ -475,3 +475,93 @@ def test_graph_ingestion_property_random_insertion_orders():
                     acc = acc + (y[gi, p] - y[gi, e])
                 assert np.array_equal(acc, delta[p])
     check()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batched Erdos-Renyi sampler: same tensor passes on the CPU here as on the GPU
+# ---------------------------------------------------------------------------------------------------------
+_CSR_FIELDS = ("ev_ptr", "ev_idx", "adj_ptr", "adj_idx", "deg", "graph_id")
+
+
+@pytest.mark.parametrize("B,P,p", [(48, 12, 0.12), (64, 5, 0.5), (16, 30, 0.05), (8, 7, 0.0), (8, 6, 1.0), (5, 1, 0.5), (1, 9, 0.3)])
+def test_sampled_batch_is_what_ingesting_its_networkx_graphs_gives(B, P, p):
+    """sample_erdos_renyi builds the CSR arrays without ever making a networkx object; rebuilding the networkx graphs
+    from its neighbour lists (``to_networkx``: G(P,p) edges in lexicographic order, then the bridges) and ingesting
+    them the usual way gives the same arrays, every graph is connected, and the bridges are exactly the reference
+    driver's chain over consecutive components (gnn_dlasso_progressive.py:186-190) with the smallest node of each."""
+    from dadmm_b200 import graph as G
+    bg = G.sample_erdos_renyi(B, P, p, "cpu", torch.Generator().manual_seed(1))
+    raw = G.sample_erdos_renyi(B, P, p, "cpu", torch.Generator().manual_seed(1), connect=False)   # same draw, no bridges
+    graphs, raw_graphs = bg.to_networkx(), raw.to_networkx()
+    assert len(bg) == B and bg.n_graphs == B and bg.P == P
+    G._cache.clear()
+    ref = G.BatchGraph.from_graph_list(graphs, P, "cpu")
+    for f in _CSR_FIELDS:
+        a, r = getattr(bg, f), getattr(ref, f)
+        assert (a is None and r is None) or torch.equal(a.to(torch.int64), r.to(torch.int64)), f
+    assert (bg.max_events, bg.max_adj) == (ref.max_events, ref.max_adj)
+    for b in range(B):
+        g, r = graphs[b], raw_graphs[b]
+        assert nx.is_connected(g) and g.number_of_nodes() == P
+        comps = sorted(nx.connected_components(r), key=min)
+        want = {(min(comps[i]), min(comps[i + 1])) for i in range(len(comps) - 1)}
+        assert {tuple(sorted(e)) for e in g.edges()} - {tuple(sorted(e)) for e in r.edges()} == want
+        assert int(bg.n_bridges[b]) == len(comps) - 1 and int(raw.n_bridges[b]) == 0
+        # the order networkx itself would hold after the driver's construction
+        d = nx.Graph()
+        d.add_nodes_from(range(P))
+        d.add_edges_from(sorted(tuple(sorted(e)) for e in r.edges()))
+        d.add_edges_from(sorted(want))
+        assert [list(d.neighbors(u)) for u in range(P)] == [list(g.neighbors(u)) for u in range(P)]
+    # propagation matrices of model #3 come out of the same lists
+    import gnn_dlasso_models_progressive as M
+    assert torch.equal(bg.normalized_adjacency(), M.normalized_adjacency(graphs, P, "cpu"))
+
+
+def test_sampler_statistics_determinism_and_argument_checks():
+    from dadmm_b200 import graph as G
+    B, P, p = 4000, 10, 0.3
+    a = G.sample_erdos_renyi(B, P, p, "cpu", torch.Generator().manual_seed(7), connect=False)
+    b = G.sample_erdos_renyi(B, P, p, "cpu", torch.Generator().manual_seed(7), connect=False)
+    c = G.sample_erdos_renyi(B, P, p, "cpu", torch.Generator().manual_seed(8), connect=False)
+    assert all(torch.equal(getattr(a, f), getattr(b, f)) for f in _CSR_FIELDS)
+    assert not torch.equal(a.deg, c.deg)
+    pairs = B * P * (P - 1) // 2
+    edges = int(a.deg.sum()) // 2
+    assert abs(edges - p * pairs) < 5 * (pairs * p * (1 - p)) ** 0.5              # binomial, 5 sigma
+    per_node = a.deg.view(B, P).double().mean(dim=0) / (P - 1)                       # no node position is favoured
+    assert float((per_node - p).abs().max()) < 5 * (p * (1 - p) / (B * (P - 1))) ** 0.5
+    # isolated nodes get chained 0-1-2-...; the complete graph needs nothing
+    chain = G.sample_erdos_renyi(3, 6, 0.0, "cpu")
+    assert [sorted(map(sorted, g.edges())) for g in chain.to_networkx()] == [[[i, i + 1] for i in range(5)]] * 3
+    full = G.sample_erdos_renyi(2, 6, 1.0, "cpu")
+    assert int(full.n_bridges.sum()) == 0 and bool((full.deg == 5).all())
+    for bad in ((0, 5, 0.5), (4, 0, 0.5), (4, 5, 1.5), (4, 5, -0.1)):
+        with pytest.raises(ValueError):
+            G.sample_erdos_renyi(*bad, "cpu")
+
+
+def test_to_networkx_round_trips_arbitrary_insertion_orders():
+    """``to_networkx`` recovers an insertion order for ANY graph this module ingested (not only sampled ones): shuffled
+    edge insertion, self-loops, isolated nodes, shared graph objects."""
+    import random
+    from dadmm_b200 import graph as G
+    rnd = random.Random(3)
+    P, graphs = 9, []
+    for s in range(12):
+        g0 = nx.erdos_renyi_graph(P, 0.35, seed=s)
+        e = list(g0.edges()) + ([(2, 2)] if s % 3 == 0 else [])
+        rnd.shuffle(e)
+        e = [(v, u) if rnd.random() < 0.5 else (u, v) for u, v in e]
+        g = nx.Graph()
+        g.add_nodes_from(range(P))
+        g.add_edges_from(e)
+        graphs.append(g)
+    graphs += [graphs[0], graphs[3]]
+    G._cache.clear()
+    bg = G.BatchGraph.from_graph_list(graphs, P, "cpu")
+    back = bg.to_networkx()
+    assert back[0] is back[-2] and back[3] is back[-1]
+    for g, r in zip(graphs, back):
+        assert [list(g.neighbors(u)) for u in range(P)] == [list(r.neighbors(u)) for u in range(P)]
+    assert [list(x.neighbors(1)) for x in bg.to_networkx([5, 0])] == [list(graphs[5].neighbors(1)), list(graphs[0].neighbors(1))]
