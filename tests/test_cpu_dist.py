@@ -105,7 +105,7 @@ def test_uneven_shards_and_one_bucket_for_gradients_and_loss_shares(tmp_path):
     for k, r in ref.items():
         assert torch.allclose(got["grads"][k], r, rtol=1e-5, atol=1e-7), k
     assert torch.allclose(got["tot32"], loss.detach(), rtol=1e-6) and got["tot64"].dtype == torch.float64
-    assert abs(float(got["tot64"]) - float(loss)) < 1e-6
+    assert abs(float(got["tot64"]) - float(loss.detach())) < 1e-6
 
 
 def test_sharded_noise_is_the_slice_of_the_full_batch_draw():
