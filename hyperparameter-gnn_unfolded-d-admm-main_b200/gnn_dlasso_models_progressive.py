@@ -72,6 +72,7 @@ class _PerSampleBatchNorm(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
+        ctx.set_materialize_grads(False)          # mean / var never carry a gradient: no zero tensors made for them
         var, mean = torch.var_mean(x, dim=1, unbiased=False, keepdim=True)
         rstd = torch.rsqrt(var + eps)
         xhat = (x - mean) * rstd
@@ -81,6 +82,8 @@ class _PerSampleBatchNorm(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gmean, _gvar):
+        if g is None:
+            return None, None, None, None
         xhat, rstd, weight = ctx.saved_tensors
         gxhat = g * weight
         gw = (g * xhat).sum(dim=(0, 1)) if ctx.needs_input_grad[1] else None
@@ -123,10 +126,9 @@ class GNNHypernetwork3(nn.Module):
                 w = _ema_weights(Bn, mom, x.device, x.dtype)            # [1,B] weights of the B sequential updates (cached)
                 keep = (1.0 - mom) ** Bn
                 # running <- keep * running + sum_b w_b stat_b, one addmm each (the running variance is the unbiased one)
-                bn.running_mean.copy_(torch.addmm(bn.running_mean.unsqueeze(0), w, mean[:, 0], beta=keep)[0])
-                bn.running_var.copy_(torch.addmm(bn.running_var.unsqueeze(0), w, var[:, 0], beta=keep,
-                                                 alpha=Pn / max(Pn - 1, 1))[0])
-                bn.num_batches_tracked += Bn
+                # (in place on a [1,C] view of the buffer: no temporary, no copy back)
+                bn.running_mean.unsqueeze(0).addmm_(w, mean[:, 0], beta=keep)
+                bn.running_var.unsqueeze(0).addmm_(w, var[:, 0], beta=keep, alpha=Pn / max(Pn - 1, 1))
         return out
 
     def forward(self, x, graph_list, adj_hat=None):
@@ -139,6 +141,12 @@ class GNNHypernetwork3(nn.Module):
             x = F.leaky_relu(getattr(self, f"conv{i}")(x, adj_hat))
             x = self._per_sample_bn(getattr(self, f"bn{i}"), x)
             x = self.dropout(x) if i < 5 else self.norm(x)
+        # the B per-sample calls of the reference bump every layer's counter B times: one fused add for the five layers
+        counters = [bn.num_batches_tracked for bn in (getattr(self, f"bn{i}") for i in range(1, 6))
+                    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None]
+        if counters:
+            with torch.no_grad():
+                torch._foreach_add_(counters, batch_size)
         return x.reshape(batch_size, -1)
 
 
