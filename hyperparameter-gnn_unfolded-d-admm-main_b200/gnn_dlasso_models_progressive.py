@@ -150,6 +150,14 @@ class GNNHypernetwork3(nn.Module):
         return x.reshape(batch_size, -1)
 
 
+    def graph_conv(self, x, nx_graph):
+        """One sample, the reference's per-sample entry point (:42-72): x [P,m,1] (or [P,m]) -> flat [P*4*hidden].
+        ``forward`` never calls it -- the batch goes through the five layers at once; a batch of one takes the same path,
+        running statistics included."""
+        x = x.squeeze(-1) if x.dim() == 3 else x
+        return self.forward(x.unsqueeze(0).unsqueeze(-1), [nx_graph]).reshape(-1)
+
+
 class DLASSO_GNNHyp3_Progressive(nn.Module):
     def __init__(self, A, args):
         super().__init__()

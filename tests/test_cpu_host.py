@@ -225,6 +225,11 @@ def test_batched_gcn_encoder_matches_per_sample_stub():
         assert torch.allclose(a, b, atol=2e-5, rtol=1e-4), float((a - b).abs().max())
         for k, v in ours.state_dict().items():
             assert torch.allclose(v.float(), theirs.state_dict()[k].float(), atol=1e-5, rtol=1e-5), k
+        # the reference's per-sample entry point (:42-72) exists here too and takes the same path with a batch of one
+        a1, b1 = ours.graph_conv(x[0], graphs[0]), theirs.graph_conv(x[0], graphs[0])
+        assert a1.shape == b1.shape == (P * 4 * h,) and torch.allclose(a1, b1, atol=5e-5, rtol=1e-4), float((a1 - b1).abs().max())
+        for k, v in ours.state_dict().items():
+            assert torch.allclose(v.float(), theirs.state_dict()[k].float(), atol=1e-5, rtol=1e-5), k
 
 
 def test_shard_ranges_cover_batch():
