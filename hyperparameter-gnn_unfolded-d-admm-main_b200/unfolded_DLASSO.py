@@ -55,9 +55,21 @@ class seq_hyperparam(nn.Module):
         self.max_param = max_param.unsqueeze(0)
         self.args = args
 
+    def _max_param_on(self, device):
+        """``max_param`` is a plain attribute in the reference (it stays on the CPU when the module moves): keep one copy
+        per device instead of a host-to-device copy in every forward; replaced or edited in place, it is copied again."""
+        src = self.max_param
+        if src.device == device:
+            return src
+        key, hit = (id(src), src._version, str(device)), self.__dict__.get("_max_param_dev")
+        if hit is None or hit[0] != key:
+            hit = (key, src.to(device))
+            self.__dict__["_max_param_dev"] = hit
+        return hit[1]
+
     def _squash(self, s):
         # s: [..., P|1, 4] pre-activation -> sigmoid * max, train-mode penalty, clamp  (:158-167)
-        h = torch.sigmoid(s) * self.max_param.to(s.device)
+        h = torch.sigmoid(s) * self._max_param_on(s.device)
         if self.training and self.args is not None:
             mean = h.sum(dim=(-2, -1), keepdim=True) / (h.shape[-2] * h.shape[-1])
             h = torch.where(mean > self.args.max_penalty_threshold, h * self.args.penalty_reduction_factor, h)
