@@ -13,14 +13,15 @@ def test_sampler_on_device_feeds_the_solver():
     import networkx as nx
     import gnn_dlasso_utils
     from dadmm_b200 import graph as G
-    model, pr = _module_case(P=6, n=256, m=64, B=96, K=4, seed=17)
+    model, pr = _module_case()          # P=3, n=512, m=160, 256 problems, K=6: the shape test_gpu_chain runs
+    B, P = len(pr["b"]), 3
     gen = torch.Generator(device=DEV).manual_seed(5)
-    bg = G.sample_erdos_renyi(96, 6, 0.25, DEV, gen)
-    assert str(bg.device) == DEV and len(bg) == 96 and bg.n_graphs == 96
+    bg = G.sample_erdos_renyi(B, P, 0.3, DEV, gen)
+    assert str(bg.device) == DEV and len(bg) == B and bg.n_graphs == B
     graphs = bg.to_networkx()
     assert all(nx.is_connected(g) for g in graphs) and int(bg.n_bridges.sum()) > 0
     G._cache.clear()
-    ref = G.BatchGraph.from_graph_list(graphs, 6, DEV)
+    ref = G.BatchGraph.from_graph_list(graphs, P, DEV)
     for f in ("ev_ptr", "ev_idx", "adj_ptr", "adj_idx", "deg", "graph_id"):
         assert torch.equal(getattr(bg, f).to(torch.int64), getattr(ref, f).to(torch.int64)), f
     assert (bg.max_events, bg.max_adj) == (ref.max_events, ref.max_adj)
