@@ -296,6 +296,8 @@ class BatchGraph:
         out.graph_id = self.graph_id[lo:hi].contiguous() if self.graph_id is not None else None
         out.B = hi - lo
         out._adj_hat = {}
+        if getattr(self, "n_bridges", None) is not None and self.graph_id is not None:
+            out.n_bridges = self.n_bridges[out.graph_id.long()]
         out.c = _lib.Graph(self.n_graphs, self.P, self.ev_ptr.data_ptr(), self.ev_idx.data_ptr(), self.deg.data_ptr(),
                            out.graph_id.data_ptr() if out.graph_id is not None else None,
                            self.adj_ptr.data_ptr(), self.adj_idx.data_ptr(), self.max_events, self.max_adj)

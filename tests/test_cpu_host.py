@@ -570,3 +570,15 @@ def test_to_networkx_round_trips_arbitrary_insertion_orders():
     for g, r in zip(graphs, back):
         assert [list(g.neighbors(u)) for u in range(P)] == [list(r.neighbors(u)) for u in range(P)]
     assert [list(x.neighbors(1)) for x in bg.to_networkx([5, 0])] == [list(graphs[5].neighbors(1)), list(graphs[0].neighbors(1))]
+
+
+def test_shard_of_a_sampled_batch_keeps_its_problems():
+    """Multi-GPU sharding of a sampled batch (``BatchGraph.shard``): the slice keeps its problems' graphs, bridge counts
+    and propagation matrices, and shares the CSR arrays."""
+    from dadmm_b200 import graph as G
+    bg = G.sample_erdos_renyi(10, 4, 0.2, "cpu", torch.Generator().manual_seed(5))
+    sh = bg.shard(3, 7)
+    assert len(sh) == 4 and sh.ev_idx.data_ptr() == bg.ev_idx.data_ptr()
+    assert torch.equal(sh.n_bridges, bg.n_bridges[3:7]) and torch.equal(sh.graph_id, bg.graph_id[3:7])
+    assert torch.equal(sh.normalized_adjacency(), bg.normalized_adjacency()[3:7])
+    assert [sorted(g.edges()) for g in sh.to_networkx()] == [sorted(g.edges()) for g in bg.to_networkx()[3:7]]
