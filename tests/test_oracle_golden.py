@@ -167,3 +167,34 @@ def test_oracle_equals_reference_on_random_configurations():
         ref_g = outs[dt][3]
         if float(ref_g.abs().max()) > 0:
             assert rel_l2(p64.grad, ref_g) < 1e-7, (case, rel_l2(p64.grad, ref_g))
+
+
+@pytest.mark.ref
+def test_committed_fixtures_are_what_the_committed_script_mints(tmp_path, monkeypatch, capsys):
+    """``oracle/make_golden.py`` run again against the unmodified reference reproduces every array of every committed
+    fixture bit for bit (inputs, fp32 and fp64 outputs, gradients).  (Skipped where the reference checkout is absent.)"""
+    import os
+    import numpy as np
+    from helpers import ROOT
+    from oracle import make_golden
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    monkeypatch.setattr("sys.argv", ["make_golden.py"])
+    state = torch.random.get_rng_state()
+    try:
+        make_golden.main()
+    finally:
+        torch.random.set_rng_state(state)
+    capsys.readouterr()
+    committed = os.path.join(ROOT, "tests", "golden")
+    names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
+    assert names == sorted(os.listdir(tmp_path)) and len(names) >= 6
+    for f in names:
+        a, b = np.load(os.path.join(committed, f), allow_pickle=True), np.load(os.path.join(tmp_path, f), allow_pickle=True)
+        assert set(a.files) == set(b.files), f
+        for k in a.files:
+            x, y = a[k], b[k]
+            assert x.shape == y.shape and x.dtype == y.dtype, (f, k)
+            if x.dtype.kind in "fiub":
+                assert np.array_equal(x, y, equal_nan=True), (f, k)
+            else:
+                assert x.tolist() == y.tolist(), (f, k)
