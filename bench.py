@@ -33,6 +33,7 @@ import networkx as nx  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "unfolded D-ADMM iterations*problems/sec (fwd+bwd)"
+METRIC_INFERENCE = "unfolded D-ADMM iterations*problems/sec (inference: no_grad forward)"
 UNIT = "iter*problems/s"
 
 WORKLOADS = {
@@ -65,13 +66,17 @@ def make_args(w):
                               penalty_reduction_factor=0.95, batch_size=w["B"], snr=4, graph_prob=w["graph_prob"])
 
 
-def make_problem(w, B, lo=0, shared_graph=False):
+def make_problem(w, B, lo=0, shared_graph=False, set_A=None):
     """Synthetic inputs in the reference's format: A via set_A (seed 0), labels/observations via the
-    set_Data recipe, graphs seeded by the GLOBAL problem index (so shards of a batch see the same graphs)."""
-    import gnn_dlasso_utils
+    set_Data recipe, graphs seeded by the GLOBAL problem index (so shards of a batch see the same graphs).
+    ``set_A``: the generator to use -- the drop-in package's by default; the CPU legs pass the reference's own (or the
+    oracle's restatement), so that they never import the product package.  All three consume the RNG identically."""
+    if set_A is None:
+        import gnn_dlasso_utils
+        set_A = gnn_dlasso_utils.set_A
     args = make_args(w)
     torch.manual_seed(0)
-    A = gnn_dlasso_utils.set_A(args)
+    A = set_A(args)
     gen = torch.Generator().manual_seed(1000 + lo)
     label = 2 * torch.randn((B, w["n"], 1), generator=gen) * (torch.rand((B, w["n"], 1), generator=gen) <= 0.25)
     if shared_graph:
@@ -146,18 +151,49 @@ def use_all_host_threads():
         torch.set_num_threads(host_threads)
 
 
-def cpu_baseline_sample(w, B_ref=None):
+def cpu_reference(w, B_ref=None, inference=False):
+    """One CPU training step of model #1 on the first B_ref problems of the workload, as a callable returning seconds.
+
+    kind "reference": the UNMODIFIED reference classes (``DLASSO_unfolded``, ``set_A``, ``compute_loss`` from
+    ``/root/reference`` or its staged copy ``oracle/_ref``, see oracle/build_ref.py) driven the way
+    unfolded_train_new.py:66-80 drives them: forward, compute_loss, loss_final.backward(), Adam step.
+    kind "port" (fallback when neither exists): the oracle's loop-faithful port of the same cost model."""
     from oracle import dadmm_oracle as O
+    from oracle import ref_harness as RH
     B_ref = B_ref or w["B_ref"]
-    args, A, label, graphs, param = make_problem(w, B_ref)
+    if RH.reference_root("unfolded_DLASSO") and RH.reference_root("gnn_dlasso_utils"):
+        ref_model, ref_utils = RH.load("unfolded_DLASSO"), RH.load("gnn_dlasso_utils")
+        args, A, label, graphs, param = make_problem(w, B_ref, set_A=ref_utils.set_A)
+        b = torch.stack([A[0, p] @ label for p in range(w["P"])], dim=1)
+        model = ref_model.DLASSO_unfolded(A, args)
+        with torch.no_grad():
+            model.seq_hyp.param.copy_(param)
+        optim = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+        def run():
+            t0 = time.perf_counter()
+            torch.manual_seed(7)
+            if inference:                       # the validation pass, unfolded_train_new.py:102-128
+                with torch.no_grad():
+                    Y, _ = model(b, graphs)
+                    ref_utils.compute_loss(Y, label)
+                return time.perf_counter() - t0
+            Y, _ = model(b, graphs)
+            _, loss_final = ref_utils.compute_loss(Y, label)
+            optim.zero_grad()
+            loss_final.backward()
+            optim.step()
+            return time.perf_counter() - t0
+        return run, B_ref, "reference"
+    args, A, label, graphs, param = make_problem(w, B_ref, set_A=O.set_A)
     b = torch.stack([A[0, p] @ label for p in range(w["P"])], dim=1)
     mp = torch.tensor([0.1, 0.99, 0.99, 0.99])
 
     def run():
         t0 = time.perf_counter()
-        O.reference_port_fwd_bwd(A, b, label, graphs, param, mp, seed=7, training=True)
+        O.reference_port_fwd_bwd(A, b, label, graphs, param, mp, seed=7, training=True, backward=not inference)
         return time.perf_counter() - t0
-    return run, B_ref
+    return run, B_ref, "port"
 
 
 def cpu_vectorised_sample(w, B_vec):
@@ -165,7 +201,7 @@ def cpu_vectorised_sample(w, B_vec):
     2L operator, autograd -- fwd+bwd on B_vec problems with all host threads.  The loop-faithful port above is bound by
     the interpreter; this one by the host's GEMM throughput."""
     from oracle import dadmm_oracle as O
-    args, A, label, graphs, param = make_problem(w, B_vec)
+    args, A, label, graphs, param = make_problem(w, B_vec, set_A=O.set_A)
     b = torch.stack([A[0, p] @ label for p in range(w["P"])], dim=1)
     AtA, Atb = O.atx(A, A), O.atx(A, b)
     gen = torch.Generator().manual_seed(7)
@@ -180,31 +216,35 @@ def cpu_vectorised_sample(w, B_vec):
 
 
 def run_reference_arm(opt, w):
-    """--impl reference: the reference's CPU cost model (oracle port, kind="port"), all host threads, bounded
-    sample per step.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (kind "reference": the unmodified classes staged
+    under oracle/_ref; kind "port" only when they are absent), all host threads, a bounded sample per step.  Rank 0 only.
+    Nothing of the product package is imported on this arm."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     use_all_host_threads()
     # size the per-step sample so that (warmup + steps) samples end within ~3 minutes: calibrate on 1 problem
-    cal, _ = cpu_baseline_sample(w, 1)
+    cal, _, _ = cpu_reference(w, 1, opt.inference)
+    cal()
     t1 = cal()
     B_ref = max(1, min(w["B_ref"], int(180.0 / ((opt.steps + opt.warmup) * t1))))
-    run, B_ref = cpu_baseline_sample(w, B_ref)
+    run, B_ref, kind = cpu_reference(w, B_ref, opt.inference)
     for _ in range(opt.warmup):
         run()
     times = [run() for _ in range(opt.steps)]
     t = sum(times) / len(times)
     value = w["K"] * B_ref / t
-    sample = f"first {B_ref} problems of {opt.workload} (K={w['K']}), one fwd+bwd per step; cost is linear in batch (Python loops per problem)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
+    sample = (f"first {B_ref} problems of {opt.workload} (K={w['K']}), one training step (forward, compute_loss, backward, Adam) per "
+              "step; the reference's cost is linear in the batch (Python loops per problem)")
+    line = {"impl": "reference", "metric": METRIC_INFERENCE if opt.inference else METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": w["B"],
                        "batch_in_sample": B_ref},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                              "host_cpus": os.cpu_count()},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_modules_loaded": sorted(m for m in sys.modules if m.startswith("dadmm_b200"))}
     emit(line)
 
 
@@ -243,8 +283,18 @@ def run_ours(opt, w):
         model.seq_hyp.param.copy_(param)
     optim = torch.optim.Adam(model.parameters(), lr=1e-4)
 
-    def step(b, label):
-        Y, _ = model(b, graphs)
+    def step(b, label, graph_arg=None):
+        g = graphs if graph_arg is None else graph_arg
+        if opt.inference:
+            # the reference's validation pass (unfolded_train_new.py:102-128): no_grad forward + compute_loss
+            with torch.no_grad():
+                Y, _ = model(b, g)
+                loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, global_batch=B_glob)
+            loss_val = loss_final.detach().clone()
+            if world > 1:
+                D.allreduce_sum_([loss_val])
+            return loss_val
+        Y, _ = model(b, g)
         # the reference's call, NaN guards included (they cost one host read of a few bytes here: gnn_dlasso_utils.compute_loss)
         loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, global_batch=B_glob)
         optim.zero_grad(set_to_none=True)
@@ -303,13 +353,17 @@ def run_ours(opt, w):
             ev.record(copy_stream)
         return b, lab, ev
 
-    def e2e_loop(n):
+    from dadmm_b200.graph import sample_erdos_renyi
+
+    def e2e_loop(n, fresh_graphs=False):
         cur = torch.cuda.current_stream(dev)
         nxt, pending, out = fetch(), None, []
         for i in range(n):
             b, lab, ev = nxt
             cur.wait_event(ev)
-            loss = step(b, lab)
+            # fresh_graphs: B new bridged G(P, p) graphs drawn, connected and ingested on the device inside the step -- the
+            # per-batch graph loop of gnn_dlasso_progressive.py:181-191 (its networkx form costs seconds per batch)
+            loss = step(b, lab, sample_erdos_renyi(B_loc, w["P"], w["graph_prob"], dev) if fresh_graphs else None)
             b.record_stream(cur)
             lab.record_stream(cur)
             if i + 1 < n:
@@ -322,10 +376,20 @@ def run_ours(opt, w):
     e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(2, min(opt.steps, 5))
+    n_e2e = max(2, opt.steps)
     e2e_loop(n_e2e)
     barrier()
     t_e2e = max_over_ranks((time.perf_counter() - t0)) / n_e2e
+    # the same loop with fresh graphs every step (the fixed-list loops above hit BatchGraph's cache: ingestion amortised)
+    t_e2e_fresh = None
+    if opt.workload != "cfg1":            # configs[0] is the one-shared-graph driver (unfolded_train_new.py:56)
+        e2e_loop(2, fresh_graphs=True)
+        barrier()
+        t0 = time.perf_counter()
+        n_fresh = max(2, min(opt.steps, 5))
+        e2e_loop(n_fresh, fresh_graphs=True)
+        barrier()
+        t_e2e_fresh = max_over_ranks((time.perf_counter() - t0)) / n_fresh
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (one extra profiled step) -------------------
     _lib.profile_enable(True)
@@ -338,35 +402,42 @@ def run_ours(opt, w):
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     t_prof = p0.elapsed_time(p1)
-    roofline, breakdown = make_roofline(w, B_loc, prof, t_prof, two_stage)
+    roofline, breakdown = make_roofline(w, B_loc, prof, t_prof, two_stage, inference=opt.inference, t_step_timed_ms=1e3 * t_dev)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     value = w["K"] * B_glob / t_dev
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
+    line = {"metric": METRIC_INFERENCE if opt.inference else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
             "ms_per_step": 1e3 * t_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if opt.algo != "fast" else "f16-operands/f32-accumulate (flagged reduced precision)", "data": "synthetic",
             "config": {"workload": w["desc"], "P": w["P"], "n": w["n"], "m": w["m"], "K": w["K"], "global_batch": B_glob,
                        "batch_per_gpu": B_loc, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "contraction": opt.algo + (" two-stage A^T(A y)" if two_stage else " AtA y"), "l2_policy": "inputs_larger_than_L2 (state tensors >> 126 MB)"
                        if B_loc * w["P"] * w["n"] * 4 > 126e6 else "working set fits L2 (small config)",
-                       "step": "forward K iters + compute_loss (NaN guards on, as the reference drivers call it) + loss_final.backward + grad allreduce + Adam",
+                       "step": ("inference: no_grad forward K iters + compute_loss (unfolded_train_new.py:102-128)" if opt.inference else
+                                "forward K iters + compute_loss (NaN guards on, as the reference drivers call it) + loss_final.backward + grad allreduce + Adam"),
+                       "graphs": "one fixed list of per-problem graphs reused every step (ingestion amortised by BatchGraph's cache); "
+                                 "e2e.fresh_graphs times the loop with new graphs drawn and ingested on the device every step",
                        "launch_chain": "classic" if opt.no_pdl else "programmatic dependent launch",
                        "operator_split": "cached with the operator (a constructor-time constant, like the reference's AtA)"},
             "clocks": clocks,
-            "e2e": {"value": w["K"] * B_glob / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e,
-                    "h2d_bytes_per_step": (b_host.numel() + label_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "e2e": {"value": w["K"] * B_glob / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e, "steps": n_e2e,
+                    "h2d_bytes_per_step": (b_host.numel() + label_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world,
+                    "fresh_graphs": None if t_e2e_fresh is None else
+                    {"value": w["K"] * B_glob / t_e2e_fresh, "unit": UNIT, "ms_per_step": 1e3 * t_e2e_fresh,
+                     "how": "dadmm_b200.graph.sample_erdos_renyi(B, P, p) per step inside the timed loop (device sampling, bridging, CSR)"}},
             "gpu_launches": launches, "loss_final": loss_val,
             "roofline": roofline, "kernel_breakdown_ms": breakdown}
     if opt.cpu_baseline and world == 1:       # rank 0 at N=1 only
         use_all_host_threads()
-        run, B_ref = cpu_baseline_sample(w)
+        run, B_ref, kind = cpu_reference(w, None, opt.inference)
         t = min(run() for _ in range(1 if w["P"] >= 50 else 2))
-        line["cpu_baseline"] = {"value": w["K"] * B_ref / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        line["cpu_baseline"] = {"value": w["K"] * B_ref / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                                 "host_cpus": os.cpu_count(),
-                                "sample": f"first {B_ref} problems of {opt.workload} (K={w['K']}), one fwd+bwd, {t:.1f} s; "
+                                "sample": f"first {B_ref} problems of {opt.workload} (K={w['K']}), one training step of the "
+                                          f"{'unmodified reference classes (oracle/_ref)' if kind == 'reference' else 'oracle port'}, {t:.1f} s; "
                                           "cost is linear in batch (Python loops per problem)"}
         B_vec = {"cfg4": 16, "cfg3": 256, "cfg5": 4}.get(opt.workload, w["B"])
         tv = cpu_vectorised_sample(w, B_vec)
@@ -377,11 +448,16 @@ def run_ours(opt, w):
         dist.destroy_process_group()
 
 
-def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False):
-    """Roofline of the dominant kernel of the step, from the profiled extra step.
-    Contraction (tensor / FMA bound): algorithmic flops per launch = 2*P*n*n*B_loc (AtA y), or 2*P*m*n*B_loc for each
-    of the two launches of the two-stage form A^T (A y)  (F = P*min(2n^2, 4mn) per contraction).
-    Step kernels (HBM bound): algorithmic bytes per iteration*problem = 20*P*n fwd, 36*P*n bwd."""
+def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False, inference=False, t_step_timed_ms=None):
+    """Roofline of the step's kernels from the profiled extra step (CUDA-event pairs around every launch of the library).
+
+    Contraction (tensor bound): algorithmic flops per launch = 2*P*n*n*B_loc (AtA y), or 2*P*m*n*B_loc for each of the two
+    launches of the two-stage form A^T (A y)  (F = P*min(2n^2, 4mn) per contraction); both launches are ONE
+    kernel (``contract_f16_kernel``) and are reported together as "contract".
+    Level kernels (HBM bound): algorithmic bytes per iteration*problem = 20*P*n forward, 36*P*n backward.
+    ``roofline`` = the kernel with the largest share of the step, whichever it is; "kernels" always lists all three, and
+    ``step_hbm_frac`` is the whole step against the HBM roofline (56*P*n*K*B bytes per training step, 20*P*n*K*B for
+    inference, over the TIMED step)."""
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -390,52 +466,51 @@ def make_roofline(w, B_loc, prof, t_step_ms, two_stage=False):
     hbm = peaks.get("hbm_gbs", 6650.0)
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    P, n = w["P"], w["n"]
+    P, n, K = w["P"], w["n"], w["K"]
     breakdown = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof.items() if v[1]}
     breakdown["step_total_ms"] = round(t_step_ms, 3)
     prof = dict(prof)
-    if prof.get("contract_stage1", (0, 0))[1]:          # two-stage contraction: both launches belong to the contraction
-        prof["contract_tc"] = (prof["contract_tc"][0] + prof["contract_stage1"][0], prof["contract_tc"][1] + prof["contract_stage1"][1])
-    def describe(kind):
-        ms, cnt = prof[kind]
-        if kind.startswith("contract"):
-            flops = 2.0 * P * (w["m"] if two_stage else n) * n * B_loc
-            ach = flops / (ms / cnt * 1e-3) / 1e12
-            note = ("fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained). The default kernel "
-                    "issues 3 fp16 MMAs per product (scaled hi/lo operand pairs), so 1/3 of this peak is its ceiling "
-                    "(3xTF32: 1/6; the SIMT kernel's ceiling is the FP32 FMA pipe, ~60-70 TFLOP/s)")
-            return {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                    "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
-                    "share_of_step": ms / t_step_ms, "note": note}
-        per = (20 if kind == "step_fwd" else 36) * P * n * B_loc
-        ach = per / (ms / cnt * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "peak_source": src, "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
-                "share_of_step": ms / t_step_ms}
-
-    # Dominant kernel.  At config 4 the two launches of the contraction together and the backward level each take a third
-    # of the step and swap places from run to run, so shares within 5 % of each other count as a tie and the tie goes to
-    # the HBM-bound level kernel (the resource BASELINE.json's metric names); the other one is reported beside it.
-    best_c = max(("contract_simt", "contract_tc"), key=lambda k: prof[k][0])
-    best_s = max(("step_fwd", "step_bwd"), key=lambda k: prof[k][0])
-    kind, other = (best_c, best_s) if prof[best_c][0] > 1.05 * prof[best_s][0] else (best_s, best_c)
-    roof = describe(kind)
-    roof["tie_rule"] = "shares within 5 % are a tie; ties go to the HBM-bound level kernel"
-    if prof[other][1]:
-        roof["runner_up"] = {k: v for k, v in describe(other).items() if k not in ("note", "peak_source", "traffic")}
-    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (same workload / batch)
+    tc = (prof["contract_tc"][0] + prof["contract_stage1"][0], prof["contract_tc"][1] + prof["contract_stage1"][1])
+    prof["contract"] = tc if tc[0] >= prof["contract_simt"][0] else prof["contract_simt"]
+    contract_kernel = "contract_f16_kernel / contract_tc*_kernel (tcgen05)" if tc[0] >= prof["contract_simt"][0] else "contract_simt_kernel (FP32 FMA)"
+    traffic = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tj.get("B") == B_loc and tj.get("P") == P and tj.get("n") == n:
-            roof["traffic"] = tj["dram_bytes_per_launch"].get("contract_tc" if kind.startswith("contract") else kind)
-            roof["traffic_source"] = tj["source"]
+            traffic = dict(tj["dram_bytes_per_launch"], source=tj["source"])
     except Exception:
         pass
-    # secondary: HBM fraction of the streaming kernels, always reported
-    for k2, per_elem in (("step_fwd", 20), ("step_bwd", 36)):
-        if prof[k2][1]:
-            m2, c2 = prof[k2]
-            roof[f"{k2}_hbm_frac"] = per_elem * P * n * B_loc / (m2 / c2 * 1e-3) / 1e9 / hbm
+
+    def describe(kind):
+        ms, cnt = prof[kind]
+        if not cnt:
+            return None
+        if kind == "contract":
+            flops = 2.0 * P * (w["m"] if two_stage else n) * n * B_loc
+            ach = flops / (ms / cnt * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": contract_kernel, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
+                    "traffic": traffic.get("contract"), "avg_launch_ms": ms / cnt, "launches_per_step": cnt, "share_of_step": ms / t_step_ms,
+                    "note": "fp32-parity contraction; peak = measured dense bf16 tcgen05 throughput (sustained).  The default kernel "
+                            "issues 3 fp16 MMAs per product (scaled hi/lo operand pairs): 1/3 of this peak is its ceiling"}
+        per = (20 if kind == "step_fwd" else 36) * P * n * B_loc
+        ach = per / (ms / cnt * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "level_fwd_kernel" if kind == "step_fwd" else "level_bwd_kernel", "achieved": ach, "peak": hbm,
+                "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(kind), "avg_launch_ms": ms / cnt, "launches_per_step": cnt,
+                "share_of_step": ms / t_step_ms}
+
+    kernels = {k: d for k in ("contract", "step_fwd", "step_bwd") if (d := describe(k)) is not None}
+    top = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    roof = dict(kernels[top])
+    roof["peak_source"] = src
+    roof["traffic_source"] = traffic.get("source")
+    roof["kernels"] = {k: {kk: vv for kk, vv in d.items() if kk != "note"} for k, d in kernels.items()}
+    for k2 in ("step_fwd", "step_bwd"):
+        if k2 in kernels:
+            roof[f"{k2}_hbm_frac"] = kernels[k2]["frac"]
+    t_ref = t_step_timed_ms if t_step_timed_ms else t_step_ms
+    step_bytes = (20 if inference else 56) * P * n * K * B_loc
+    roof["step_hbm_frac"] = step_bytes / (t_ref * 1e-3) / 1e9 / hbm
+    roof["step_algorithmic_bytes"] = step_bytes
     return roof, breakdown
 
 
@@ -473,6 +548,8 @@ def main():
                     help="contraction kernel; 'fast' is the FLAGGED reduced-precision mode (fp16 operands, 1e-2 class) and is "
                          "never the default: the headline number is measured in fp32-parity mode")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--inference", action="store_true",
+                    help="time the no_grad forward sweep + compute_loss instead of a training step (BASELINE configs[4]: --workload cfg5)")
     ap.add_argument("--batch", type=int, default=None,
                     help="diagnostic: override the workload's global batch (the reported config then names it)")
     ap.add_argument("--no-pdl", action="store_true", help="A/B switch: launch the K-loop chain without programmatic dependent launch")

@@ -60,6 +60,10 @@ static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, S
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t budget = 100 * 1024;  // two CTAs per SM
     int TB = std::max(1, std::min(B, (16 + P - 1) / P));
+    {
+        static const int forced = [] { const char* e = getenv("DADMM_STEP_TB"); return e ? atoi(e) : 0; }();   // experiment knob
+        if (forced > 0) TB = std::max(1, std::min(B, forced));
+    }
     for (int vec = max_vec; vec >= 1; vec >>= 1) {
         if (n % vec) continue;
         for (int tb = TB; tb >= 1; --tb) {

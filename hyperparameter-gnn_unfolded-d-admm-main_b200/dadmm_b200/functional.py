@@ -50,6 +50,16 @@ def _algo(algo) -> int:
     return _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
 
 
+def same_dtype(what: str, like: torch.Tensor, **tensors) -> None:
+    """Every pointer handed to the C ABI is read as ``like``'s dtype: a tensor of another dtype (an fp16 hypernetwork
+    output under ``torch.autocast``, a float64 operator next to float32 states) would be read as garbage -- or, for an
+    output, written out of bounds -- without any error on the device.  Raise here instead."""
+    for name, t in tensors.items():
+        if t is not None and t.dtype != like.dtype:
+            raise _lib.DadmmError(f"{what}: `{name}` is {t.dtype} but the states are {like.dtype}; every tensor passed by "
+                                  "pointer must share one dtype (float32 or float64)")
+
+
 def _state3(t: torch.Tensor) -> torch.Tensor:
     """[B,P,n,1] or [B,P,n] -> contiguous [B,P,n] view/copy."""
     if t.dim() == 4:
@@ -118,6 +128,7 @@ def step_fwd(graph: BatchGraph, clamps, hyp, y, U, delta, AtAy, Atb, want_delta=
     """One D-ADMM iteration on [B,P,n] tensors; ``delta=None`` recomputes clampD(2L y).
     Returns (y_next, U_next|None, delta_next|None, grad_raw|None)."""
     dev = require_cuda(y, U, delta, AtAy, Atb, hyp)
+    same_dtype("step_fwd", y, U=U, delta=delta, AtAy=AtAy, Atb=Atb, hyp=hyp)
     B, P, n = y.shape
     y_next = torch.empty_like(y)
     U_next = torch.empty_like(y) if want_U else None
@@ -136,6 +147,8 @@ def step_bwd(graph: BatchGraph, clamps, hyp, y, U, delta, graw, y_next, gy_next,
              per_sample: bool, label=None, loss_coef: float = 0.0):
     """Backward of ``step_fwd``.  Returns (gy_direct, gAtAy, gU, gdelta, ghyp) with ghyp shaped like hyp."""
     dev = require_cuda(y, U, graw, y_next)
+    same_dtype("step_bwd", y, U=U, delta=delta, grad_raw=graw, y_next=y_next, gy_next=gy_next, gU_next=gU_next,
+               gdelta_next=gdelta_next, hyp=hyp, label=label)
     B, P, n = y.shape
     dt = dtype_code(y)
     gy, ga, gU, gd = (torch.empty_like(y) for _ in range(4))
@@ -164,11 +177,13 @@ class Contract(torch.autograd.Function):
     """y [B,P,n] -> W y; backward Wt g (Wt = W^T, passed explicitly so no transpose is re-materialised)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, W, Wt, algo):
         ctx.Wt, ctx.algo = Wt, algo
         return contract(W, x, algo=algo)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
         return contract(ctx.Wt, g.contiguous(), algo=ctx.algo), None, None, None
 
@@ -178,6 +193,7 @@ class Step(torch.autograd.Function):
     Inputs y, U, delta, AtAy, Atb [B,P,n]; hyp [B,4,P] or [P,4].  Outputs (y+, U+, delta+)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, y, U, delta, AtAy, Atb, hyp, graph, clamps, flags):
         y, U, delta, AtAy, Atb, hyp = (t.contiguous() for t in (y, U, delta, AtAy, Atb, hyp))
         y_next, U_next, d_next, graw = step_fwd(graph, clamps, hyp, y, U, delta, AtAy, Atb, flags=flags)
@@ -186,12 +202,42 @@ class Step(torch.autograd.Function):
         return y_next, U_next, d_next
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy_next, gU_next, gd_next):
         y, U, delta, graw, y_next, hyp = ctx.saved_tensors
-        c = lambda t: None if t is None else t.contiguous()
+        c = lambda t: None if t is None else t.contiguous().to(y.dtype)
         gy, ga, gU, gd, ghyp = step_bwd(ctx.graph, ctx.clamps, hyp, y, U, delta, graw, y_next, c(gy_next), c(gU_next),
                                         c(gd_next), per_sample=(hyp.dim() == 3))
         return gy, gU, gd, ga, None, ghyp, None, None, None
+
+
+def solver_operators(cache: dict, A: torch.Tensor, device, dtype):
+    """(A, AtA [P,n,n], AtA^T, A^T [P,n,m]) on ``device`` in the dtype of the states, for the modules' ``A`` attribute
+    (reference unfolded_DLASSO.py:12-16: ``A`` is a plain attribute, ``AtA`` is computed from it once).  One entry per
+    device, validated against the identity and version of ``A`` -- assigning a new ``model.A`` or writing to it in place
+    rebuilds the operators (and frees the previous ones); the states are drawn by ``torch.randn`` in the default dtype, so
+    an ``A`` of another dtype is cast to it here, as every tensor handed to the library must share one dtype."""
+    dev = torch.device(device)
+    key = (dtype, id(A), A._version)
+    hit = cache.get(str(dev))
+    if hit is None or hit[0] != key:
+        Ad = A.detach().to(device=dev, dtype=dtype)
+        W = atx(Ad, Ad)[0].contiguous()                 # AtA_p = A_p^T A_p   (reference :16)
+        Wt = W.transpose(1, 2).contiguous()
+        if torch.equal(W, Wt):
+            Wt = W
+        At = Ad[0].transpose(1, 2).contiguous()         # [P,n,m]: K-major operator for Atb on the tensor-core path
+        hit = (key, (Ad, W, Wt, At))
+        cache[str(dev)] = hit
+    return hit[1]
+
+
+def clear_caches() -> None:
+    """Release the process-wide caches: persistent operator splits (``_OpSplitCache``) and ingested graph batches
+    (``graph._cache``).  The modules' own operator caches (``model._ops``) go with the module."""
+    from . import graph as _graph
+    _op_splits.entries.clear()
+    _graph._cache.clear()
 
 
 def _factor_struct(factor, P, n, like):
@@ -257,11 +303,15 @@ class Unfolded(torch.autograd.Function):
     reference has no other differentiable input on this path)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, hyp, W, Wt, Atb, y0, U0, d0, graph, clamps, algo, flags, handle, factor=None, factor_t=None):
         """factor = (F1 [P,m,n], F2 [P,n,m][, rhs [B,P,m]]) with W = F2 F1 (and Atb = F2 rhs), factor_t likewise for Wt
         (``dadmm_factor``): lets the library evaluate the contraction in two stages when that is cheaper
         (AtA = A^T A: F1 = A, F2 = A^T, rhs = b)."""
-        dev = require_cuda(hyp, W, Atb, y0, U0, d0)
+        dev = require_cuda(hyp, W, Wt, Atb, y0, U0, d0)
+        same_dtype("Unfolded", y0, hyp=hyp, W=W, Wt=Wt, Atb=Atb, U0=U0, d0=d0)
+        if handle is not None:
+            handle.pending = None         # an offer no reverse sweep collected belongs to an earlier forward pass
         hyp, y0, U0, d0 = (t.contiguous() for t in (hyp, y0, U0, d0))
         Atb = Atb.contiguous() if Atb is not None else None      # None: only with a factor rhs on the two-stage route
         K, P, _ = hyp.shape
@@ -304,6 +354,7 @@ class Unfolded(torch.autograd.Function):
         return Y
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gY):
         hyp, Wt, y0, U0, d0, Y, U_save, R_save = ctx.saved_tensors
         dev = Y.device
@@ -320,7 +371,7 @@ class Unfolded(torch.autograd.Function):
             if gY is not None and gY.data_ptr() == sentinel.data_ptr():
                 gY = None       # zero placeholder emitted by MSELoss.backward: gradient arrives through (label, coef)
         if gY is not None:
-            gY = gY.contiguous()
+            gY = gY.contiguous().to(Y.dtype)
         ghyp = torch.empty_like(hyp)
         fac_t = ctx.fac_t
         with device_guard(dev):
@@ -409,8 +460,11 @@ class MSELoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Y, label, B_norm, handle):
+        same_dtype("MSELoss", Y, label=label)
         ctx.save_for_backward(Y, label)
         ctx.B_norm, ctx.handle = B_norm, handle
+        if handle is not None:
+            handle.pending = None         # a (label, coef) offer is valid for the backward pass of THIS loss only
         return loss_per_iteration(Y, label, B_norm, handle)
 
     @staticmethod

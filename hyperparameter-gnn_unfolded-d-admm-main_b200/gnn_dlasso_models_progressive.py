@@ -186,17 +186,8 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         self.check_finite = True
         self._ops = {}
 
-    def _operators(self, device):
-        key = str(device)
-        if key not in self._ops:
-            A = self.A.detach().to(device)
-            W = DF.atx(A, A)[0].contiguous()
-            Wt = W.transpose(1, 2).contiguous()
-            if torch.equal(W, Wt):
-                Wt = W
-            At = A[0].transpose(1, 2).contiguous()      # [P,n,m]: K-major operator for Atb on the tensor-core path
-            self._ops[key] = (A, W, Wt, At)
-        return self._ops[key]
+    def _operators(self, device, dtype=None):
+        return DF.solver_operators(self._ops, self.A, device, dtype or torch.get_default_dtype())
 
     @property
     def AtA(self):
@@ -227,8 +218,10 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
             self._scale_key = key
         return torch.clamp(h * self._scale_vec, max=self._cap_vec)
 
-    def forward(self, b, graph_list, training_iterations=None):
-        """b [B,P,m,1] -> (Y [K,B,P,n,1], (alpha_k, tau_k, rho_k, eta_k) of the last iteration)."""
+    def forward(self, b, graph_list, training_iterations=None, noise=None):
+        """b [B,P,m,1] -> (Y [K,B,P,n,1], (alpha_k, tau_k, rho_k, eta_k) of the last iteration).
+        ``noise`` (not in the reference): initial (y, U, delta) [B,P,n,1] each, replacing the three ``randn * 1e-2`` draws
+        (batch-sharded runs pass their slice of the full batch's draws, ``dadmm_b200.dist.sharded_noise``)."""
         if len(b) != len(graph_list):
             raise ValueError(f"len(b)={len(b)} != len(graph_list)={len(graph_list)}")
         K = training_iterations if training_iterations is not None else self.K
@@ -238,9 +231,12 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         Atb = DF.contract(At, b.to(W.dtype).squeeze(-1), algo=self.contract_algo).unsqueeze(-1)   # [B,P,n,1]
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         adj_hat = graph.normalized_adjacency(W.dtype)                 # cached on the BatchGraph (itself cached per graph_list)
-        y0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
-        U0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
-        d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
+        if noise is None:
+            y0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
+            U0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
+            d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
+        else:
+            y0, U0, d0 = (t.to(device=device, dtype=W.dtype).reshape(B, self.P, self.n, 1) for t in noise)
         flags = torch.zeros(max(K, 1), dtype=torch.int32, device=device) if self.check_finite else None
         out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, flags, guarded=False)
         if flags is not None:

@@ -105,17 +105,8 @@ class DLASSO_unfolded(nn.Module):
         self._ops = {}                   # device -> (A, AtA [P,n,n], AtA^T [P,n,n])
 
     # ------------------------------------------------------------------ operators
-    def _operators(self, device):
-        key = str(device)
-        if key not in self._ops:
-            A = self.A.detach().to(device)
-            W = DF.atx(A, A)[0].contiguous()            # AtA_p = A_p^T A_p   (reference :16)
-            Wt = W.transpose(1, 2).contiguous()
-            if torch.equal(W, Wt):
-                Wt = W
-            At = A[0].transpose(1, 2).contiguous()      # [P,n,m]: K-major operator for Atb on the tensor-core path
-            self._ops[key] = (A, W, Wt, At)
-        return self._ops[key]
+    def _operators(self, device, dtype=None):
+        return DF.solver_operators(self._ops, self.A, device, dtype or torch.get_default_dtype())
 
     @property
     def AtA(self):
@@ -124,8 +115,12 @@ class DLASSO_unfolded(nn.Module):
         return self._operators(dev)[1].unsqueeze(0).to(self.A.device)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, b, graph_list, K=None):
-        """b [B,P,m,1]; graph_list: B graphs over nodes 0..P-1.  Returns (Y [K,B,P,n,1], hyp [P|1,4,1])."""
+    def forward(self, b, graph_list, K=None, noise=None):
+        """b [B,P,m,1]; graph_list: B graphs over nodes 0..P-1.  Returns (Y [K,B,P,n,1], hyp [P|1,4,1]).
+
+        ``noise`` (not in the reference): the initial (y, U, delta), each [B,P,n,1], in place of the three ``randn * 1e-2``
+        draws -- a rank of a batch-sharded job passes its slice of the full batch's draws (``dadmm_b200.dist.sharded_noise``)
+        so that N ranks reproduce the single-process run."""
         if len(b) != len(graph_list):
             raise ValueError(f"len(b)={len(b)} != len(graph_list)={len(graph_list)}")
         batch_size, device = len(b), b.device
@@ -136,9 +131,12 @@ class DLASSO_unfolded(nn.Module):
         Atb = None if self._residual_from_factor(W, batch_size) else self._atb(At, b, W.dtype)
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         # initial noise: same three draws, same order / shape / device as the reference (:49-51)
-        y0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
-        U0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
-        d0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
+        if noise is None:
+            y0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
+            U0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
+            d0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
+        else:
+            y0, U0, d0 = (t.to(device=device, dtype=W.dtype).reshape(batch_size, self.P, self.n, 1) for t in noise)
         table = self.seq_hyp.table(K)                                   # [K, P|1, 4]
         Y = self._run(table, W, Wt, Atb, y0, U0, d0, graph, K, b)
         return Y, table[K - 1].unsqueeze(-1)

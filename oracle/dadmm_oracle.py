@@ -18,6 +18,7 @@ follows (paths relative to the reference checkout):
   accumulation order) and ``delta_dense`` (``2*L @ y``, vectorised)
 * ``gnn_dlasso_models_progressive.py:198-232`` (model #3 recurrence)    -> ``step`` with fixed clamps
 * ``gnn_dlasso_utils.py:27-88``  (``compute_loss``)                     -> ``loss``
+* ``gnn_dlasso_utils.py:4-16``   (``set_A``)                            -> ``set_A``
 
 Pinning: ``oracle/make_golden.py`` runs the UNMODIFIED reference classes (imported
 from ``/root/reference`` in the build container, ``torch_geometric`` stubbed) and
@@ -38,6 +39,19 @@ import numpy as np
 import torch
 
 INF = float("inf")
+
+
+# --------------------------------------------------------------------------------------
+# problem generator
+# --------------------------------------------------------------------------------------
+def set_A(args) -> torch.Tensor:
+    """gnn_dlasso_utils.py:4-16: per agent ``randn(m,n)`` -> SVD -> singular values clamped to [0.1, 10] ->
+    ``U diag(S) V^T``; A [1,P,m,n] fp32 on the CPU.  Same RNG consumption as the reference (one draw per agent)."""
+    A = torch.zeros((1, args.P, args.m, args.n))
+    for p in range(args.P):
+        U, S, V = torch.svd(torch.randn((args.m, args.n)))
+        A[0, p] = U @ torch.diag(torch.clamp(S, min=0.1, max=10.0)) @ V.T
+    return A
 
 
 # --------------------------------------------------------------------------------------
@@ -280,7 +294,7 @@ def delta_loops_autograd(graph_list: Sequence, y: torch.Tensor) -> torch.Tensor:
 
 
 def reference_port_fwd_bwd(A, b, label, graph_list, param, max_param, seed: int = 7,
-                           training: bool = True):
+                           training: bool = True, backward: bool = True):
     """Loop-faithful CPU port of one training step of model #1 (forward through K iterations,
     ``loss_final.backward()``): per-agent matmul loops, Python neighbour loops, autograd.
     Returns (Y, loss_final, param.grad).  Used ONLY as bench.py's CPU baseline / reference arm."""
@@ -306,5 +320,7 @@ def reference_port_fwd_bwd(A, b, label, graph_list, param, max_param, seed: int 
         Y.append(y)
     Y = torch.stack(Y)
     _, lf = loss(Y, label)
+    if not backward:              # validation pass (unfolded_train_new.py:102-128)
+        return Y.detach(), lf.detach(), None
     lf.backward()
     return Y.detach(), lf.detach(), param.grad

@@ -24,10 +24,22 @@ import torch
 import torch.nn as nn
 
 REFERENCE_ROOT = os.environ.get("DADMM_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py (travels to the GPU box)
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "unfolded_DLASSO.py"))
+
+
+def reference_root(name: str = "unfolded_DLASSO") -> str:
+    """Directory ``name``.py is imported from: the reference checkout where it exists (build container), else the
+    unmodified copies staged under ``oracle/_ref`` (digests checked against the manifest).  '' when neither has it."""
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, name + ".py")):
+        return REFERENCE_ROOT
+    from . import build_ref
+    if build_ref.staged() and os.path.isfile(os.path.join(STAGED_ROOT, name + ".py")):
+        return STAGED_ROOT
+    return ""
 
 
 class _StubGCNConv(nn.Module):
@@ -83,12 +95,13 @@ _ref_cache = {}
 def load(name: str):
     """Import reference module ``name`` (e.g. 'unfolded_DLASSO') under a private alias so that it
     cannot shadow / be shadowed by the same-named drop-in modules of the product package."""
-    if not reference_available():
-        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
     if name in _ref_cache:
         return _ref_cache[name]
+    root = reference_root(name)
+    if not root:
+        raise RuntimeError(f"reference module {name}.py found neither at {REFERENCE_ROOT} nor staged under {STAGED_ROOT}")
     _install_stubs()
-    spec = importlib.util.spec_from_file_location(f"_dadmm_ref_{name}", os.path.join(REFERENCE_ROOT, name + ".py"))
+    spec = importlib.util.spec_from_file_location(f"_dadmm_ref_{name}", os.path.join(root, name + ".py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     _ref_cache[name] = mod
