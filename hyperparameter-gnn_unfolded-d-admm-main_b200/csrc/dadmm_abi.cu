@@ -14,6 +14,8 @@
 #include "contract_f16.cuh"
 #include "step.cuh"
 #include "unfolded.cuh"
+#include "unfolded_lean.cuh"
+#include "unfolded_pipe.cuh"
 
 namespace dadmm {
 thread_local char g_err[512] = "";
@@ -309,6 +311,50 @@ static bool level_ten_warps(int rows) {
     return (rows % 8) != 0 && (rows % 10) == 0;
 }
 
+// second-generation lean level kernels (unfolded_lean.cuh: packed fp32 arithmetic, byte-offset lists); DADMM_LEVEL_GEN=1
+// keeps the first generation (A/B measurements)
+static bool lean_gen2() {
+    static const bool on = [] { const char* e = getenv("DADMM_LEVEL_GEN"); return !(e && atoi(e) == 1); }();
+    return on;
+}
+
+// CTAs per SM the lean kernels' registers are budgeted for: DADMM_LEAN_MINB_FWD / _BWD override the defaults
+static int lean_minb(bool fwd) {
+    static const int f = [] { const char* e = getenv("DADMM_LEAN_MINB_FWD"); return e ? atoi(e) : 0; }();
+    static const int b = [] { const char* e = getenv("DADMM_LEAN_MINB_BWD"); return e ? atoi(e) : 0; }();
+    return fwd ? (f ? f : 5) : (b ? b : 4);
+}
+template <typename K, typename Prm>
+static int launch_level(K kernel, int grid, int threads, size_t smem, cudaStream_t s, const Prm& p) {
+    if (int e = allow_smem(kernel, smem)) return e;
+    DADMM_CUDA(launch_chain(kernel, dim3(grid), dim3(threads), smem, s, p));
+    return 0;
+}
+
+static int sm_count() {
+    static const int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+// forward level as a persistent TMA pipeline (unfolded_pipe.cuh); DADMM_FWD_PIPE=0 keeps the occupancy-driven kernels
+static bool fwd_pipe_enabled() {
+    static const bool on = [] { const char* e = getenv("DADMM_FWD_PIPE"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+// problems per tile of the pipelined kernel: as many as keep the tile at or below 64 rows, dividing the batch
+static int pipe_tb(int B, int P) {
+    static const int forced = [] { const char* e = getenv("DADMM_PIPE_TB"); return e ? atoi(e) : 0; }();
+    int best = 1;
+    for (int d = 1; d * P <= 64 && d <= B; ++d)
+        if (B % d == 0) best = d;
+    if (forced > 0 && B % forced == 0) best = forced;
+    return best;
+}
+
 template <typename T>
 static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, const dadmm_clamps* cl_k,
                           const dadmm_clamps* cl_prev, const void* hyp_k, const void* hyp_prev, const void* y,
@@ -358,7 +404,37 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                 p.sq_part = sq_part;
                 if (sums_grid) *sums_grid = c.grid;
             }
-            if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level)
+            if (lean && !p.first && fwd_pipe_enabled() && lean_gen2()) {
+                const int tb = pipe_tb(B, P);
+                const size_t psmem = pipe::fwd_smem_bytes(tb, P, std::max(g->max_events, 1));
+                if (psmem <= 227 * 1024) {
+                    static const int ncons = [] { const char* e = getenv("DADMM_PIPE_WARPS"); return e ? atoi(e) : 16; }();
+                    p.TB = tb;
+                    p.list_cap = std::max(g->max_events, 1);
+                    p.csplit = 1;
+                    const long long tiles = (long long)(B / tb) * (n / 128);
+                    const int grid = (int)std::min<long long>(sm_count(), tiles);
+                    if (agent_sum && sq_part) {
+                        p.agent_sum = (T*)agent_sum;
+                        p.sq_part = sq_part;
+                        if (sums_grid) *sums_grid = grid;
+                    }
+                    if (int e = ncons == 8    ? launch_level(pipe::level_fwd_pipe_kernel<8>, grid, 9 * 32, psmem, s, p)
+                                : ncons == 12 ? launch_level(pipe::level_fwd_pipe_kernel<12>, grid, 13 * 32, psmem, s, p)
+                                              : launch_level(pipe::level_fwd_pipe_kernel<16>, grid, 17 * 32, psmem, s, p))
+                        return e;
+                    DADMM_LAUNCHED();
+                    return 0;
+                }
+            }
+            if (lean && !p.first && p.list_cap > 0 && lean_gen2()) {
+                const int mb = lean_minb(true);
+                if (int e = mb == 3   ? launch_level(lean::level_fwd_lean_kernel<kStepThreads, 3>, c.grid, kStepThreads, smem, s, p)
+                            : mb == 4 ? launch_level(lean::level_fwd_lean_kernel<kStepThreads, 4>, c.grid, kStepThreads, smem, s, p)
+                                      : launch_level(lean::level_fwd_lean_kernel<kStepThreads, 5>, c.grid, kStepThreads, smem, s, p))
+                    return e;
+            }
+            else if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level)
             else DADMM_LAUNCH_LFWD(4, false, kStepThreads)
             launched = true;
         }
@@ -413,7 +489,20 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
         if (c.vec == 4) {
             // lean form: the fused fp16 training path on full tiles, levels k >= 1 (see level_bwd_kernel)
             const bool lean = !p.first && graw_is_residual && !p.hasD && !gY_prev && (n % 128) == 0 && (B % c.TB) == 0;
-            if (lean && level_ten_warps(c.TB * P)) DADMM_LAUNCH_LBWD(4, true, 320)
+            static const bool bwd_gen1 = [] { const char* e = getenv("DADMM_BWD_GEN"); return e && atoi(e) == 1; }();
+            if (lean && p.list_cap > 0 && lean_gen2() && !bwd_gen1) {
+                const int mb = lean_minb(false);
+                if (level_ten_warps(c.TB * P)) {
+                    if (int e = mb <= 2 ? launch_level(lean::level_bwd_lean_kernel<320, 2>, c.grid, 320, smem, s, p)
+                                        : launch_level(lean::level_bwd_lean_kernel<320, 3>, c.grid, 320, smem, s, p))
+                        return e;
+                } else {
+                    if (int e = mb <= 3 ? launch_level(lean::level_bwd_lean_kernel<kStepThreads, 3>, c.grid, kStepThreads, smem, s, p)
+                                        : launch_level(lean::level_bwd_lean_kernel<kStepThreads, 4>, c.grid, kStepThreads, smem, s, p))
+                        return e;
+                }
+            }
+            else if (lean && level_ten_warps(c.TB * P)) DADMM_LAUNCH_LBWD(4, true, 320)
             else if (lean) DADMM_LAUNCH_LBWD(4, true, kStepThreads)
             else DADMM_LAUNCH_LBWD(4, false, kStepThreads)
             launched = true;
@@ -446,7 +535,7 @@ static size_t amax_slots_bytes(int K) { return ((size_t)(K + 1) * 4 + 255) / 256
 static size_t sq_part_bytes(int dtype, int B, int P, int n, int K) {
     StepCfg c;
     if (dtype != DADMM_F32 || step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), &c)) return 0;
-    const size_t grid = (size_t)((B + c.TB - 1) / c.TB) * c.nchunks;         // upper bound of the level grid
+    const size_t grid = std::max<size_t>((size_t)((B + c.TB - 1) / c.TB) * c.nchunks, 192);   // upper bound of the level grid
     return ((size_t)K * grid * sizeof(double) + 255) / 256 * 256;
 }
 

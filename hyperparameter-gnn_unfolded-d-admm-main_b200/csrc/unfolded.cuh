@@ -268,6 +268,15 @@ __device__ __forceinline__ void stage_scalars(T* sHyp, T* sDeg, int TB, int P, i
     }
 }
 
+// any non-finite entry in one table row -> all flag bits: a non-finite alpha_k makes y_{k+1} non-finite without touching
+// y_k, U_k or r_k, the quantities the level kernels watch (reference guard unfolded_DLASSO.py:102-104)
+template <typename T>
+__device__ __forceinline__ void flag_nonfinite_row(const T* __restrict__ hyp_row, int P, int32_t* flags) {
+    if (flags && blockIdx.x == 0)
+        for (int q = threadIdx.x; q < 4 * P; q += blockDim.x)
+            if (!isfinite(__ldg(hyp_row + q))) atomicOr(flags, 0xF);
+}
+
 // LEAN: the configuration of the fused fp16 training/inference path on full tiles -- a already holds AtA y - Atb
 // (no Atb stream), r_k is not written, no delta clamp, n % (32 VEC) == 0 and B % TB == 0 (no lane / problem guards).
 // ncu (round 1) showed the generic form executing 366 straight-line instructions per 128-unknown row segment, a
@@ -304,6 +313,7 @@ level_fwd_kernel(const LevelFwdParams<T> p) {
     const bool staged = p.list_cap > 0;
     if (!first && staged) stage_lists<T, VEC>(sPtr, sIdx, p.TB, P, p.B, b0, p.list_cap, p.lst_ptr, p.lst_idx, p.gid);
     stage_scalars<T>(sHyp, sDeg, p.TB, P, p.B, b0, p.hyp_k, p.hyp_prev, p.deg, p.gid);
+    flag_nonfinite_row<T>(p.hyp_k, P, p.flags);
     pdl_wait();
     pdl_trigger();
 

@@ -193,8 +193,9 @@ class DLASSO_unfolded(nn.Module):
             y_n, U_n, d_n = DF.Step.apply(y, U, d, a, Atb, hyp[k], graph, clamps, flag)
             if int(flag) & 4:
                 print(f"Warning: NaN/Inf in gradient at iteration {k}, skipping update...")
-                # grad := 0  =>  y_next = clamp(y_k); consensus / dual update as usual (:86-99)
-                y_n = torch.clamp(y, -clamps[1], clamps[1])
+                # grad := 0  =>  y_next = clamp(y_k - alpha_k * 0); consensus / dual update as usual (:86-99).  The product is
+                # kept: a non-finite alpha_k makes y_next non-finite here exactly as in the reference (-> the :102-104 guard)
+                y_n = torch.clamp(y - hyp[k][:, 0].reshape(1, -1, 1) * torch.zeros_like(y), -clamps[1], clamps[1])
                 d_n = self.compute_delta(None, y_n.unsqueeze(-1), _graph=graph).squeeze(-1)
                 U_n = torch.clamp(U + d_n * hyp[k][:, 3].reshape(1, -1, 1), -clamps[3], clamps[3])
             if bad(y_n):

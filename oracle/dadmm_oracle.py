@@ -156,6 +156,13 @@ def contract(AtA: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def contract_gemm(AtA: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Same product as ``contract`` as ONE batched GEMM per call (``AtA_p [n,n] @ Y_p [n,B]``) instead of the reference's
+    B broadcast mat-vecs per agent -- identical up to summation order (1e-15 in fp64, where this form is used: the fp64
+    checker of the GPU tests at the BASELINE shapes, which would otherwise spend minutes in memory-bound GEMVs)."""
+    return torch.einsum("pij,bpj->bpi", AtA[0], y[..., 0]).unsqueeze(-1)
+
+
 # --------------------------------------------------------------------------------------
 # hyper-parameter table (model #1)
 # --------------------------------------------------------------------------------------
@@ -221,14 +228,15 @@ def step(AtAy, Atb, deg, y, U, delta, alpha, tau, rho, eta, c: Clamps, delta_fn)
 
 
 def unfolded_forward(AtA, Atb, graph_list, y0, U0, d0, hyp, clamp_fn=clamps_model1,
-                     exact_delta: bool = False, keep: bool = False):
+                     exact_delta: bool = False, keep: bool = False, gemm_contract: bool = False):
     """K-iteration recurrence of ``DLASSO_unfolded.forward`` (unfolded_DLASSO.py:53-109) given
     the initial noise (y0,U0,d0) and a hyper-parameter table ``hyp`` [K,P,4] (shared over the
     batch, model #1) or [K,B,P,4] (per sample, model #3 with frozen hypernetwork output).
 
     exact_delta=True uses the reference's accumulation order (bit-faithful, no autograd);
     otherwise the dense 2L einsum (differentiable).  Returns Y [K,B,P,n,1] (+ per-iteration
-    (y,U,delta,grad_raw,AtAy) inputs when keep=True).  The NaN/Inf guards of
+    (y,U,delta,grad_raw,AtAy) inputs when keep=True).  gemm_contract=True evaluates the contraction as one batched GEMM
+    (``contract_gemm``: same values up to summation order).  The NaN/Inf guards of
     unfolded_DLASSO.py:55-61,84-86,102-104 are no-ops for finite data and are omitted here;
     ``tests/test_nan_guard.py`` covers them through the guarded path."""
     B, P = y0.shape[0], y0.shape[1]
@@ -248,7 +256,7 @@ def unfolded_forward(AtA, Atb, graph_list, y0, U0, d0, hyp, clamp_fn=clamps_mode
             al, ta, rh, et = (h[:, i].reshape(1, P, 1, 1) for i in range(4))
         else:                 # [B,P,4] -> [B,P,1,1]
             al, ta, rh, et = (h[:, :, i].reshape(B, P, 1, 1) for i in range(4))
-        a = contract(AtA, y)
+        a = contract_gemm(AtA, y) if gemm_contract else contract(AtA, y)
         y_n, U_n, d_n, g_raw = step(a, Atb, deg, y, U, d, al, ta, rh, et, clamp_fn(k), dfn)
         if keep:
             trace.append(dict(y=y, U=U, delta=d, AtAy=a, grad_raw=g_raw, y_next=y_n, U_next=U_n, delta_next=d_n))
@@ -258,12 +266,17 @@ def unfolded_forward(AtA, Atb, graph_list, y0, U0, d0, hyp, clamp_fn=clamps_mode
     return (Y, trace) if keep else Y
 
 
-def loss(Y: torch.Tensor, label: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def loss(Y: torch.Tensor, label: torch.Tensor, vectorised: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """gnn_dlasso_utils.py:27-88 for finite inputs: ``losses[k] = mean_p mse(Y[k,:,p], label)``;
-    returns (mean_k + 1e-8, last + 1e-8)."""
+    returns (mean_k + 1e-8, last + 1e-8).  vectorised=True evaluates the K*P ``mse_loss`` slices as one reduction (same
+    values up to summation order): autograd through the slice form allocates a full-size zero tensor per slice, which at
+    the BASELINE shapes (K*P = 1250 slices of a GB-sized Y) is minutes of memory traffic in the fp64 checker."""
     K, B, P, n, _ = Y.shape
     Yr = Y.reshape(K, B, P, n)
     lab = label.reshape(B, n)
+    if vectorised:
+        losses = ((Yr - lab.reshape(1, B, 1, n)) ** 2).mean(dim=(1, 3)).sum(dim=1) / P
+        return losses.mean() + 1e-8, losses[-1] + 1e-8
     losses = []
     for k in range(K):
         acc = 0.0

@@ -15,10 +15,10 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-MODEL1_CASES = ["m1_zero_P5_n64", "m1_trained_P5_n500", "m1_same_pergraph_P8_n48", "m1_trained15_P5_n51"]
+MODEL1_CASES = ["m1_zero_P5_n64", "m1_trained_P5_n500", "m1_same_pergraph_P8_n48", "m1_trained15_P5_n51", "m1_cfg4like_P12_n40"]
 MODEL3_CASES = ["m3_frozen_P5_n32"]
-# minted after the round-1 GPU budget was spent: pinned by the CPU oracle tests now, to join the GPU lists in round 2
-MODEL1_EXTRA_CASES = ["m1_cfg4like_P12_n40"]
+# the config-4-like miniature (12 agents, sparse bridged per-problem graphs) is also kept under its own name
+MODEL1_EXTRA_CASES = []
 
 
 def graph_from_adj(ptr, idx, P):
