@@ -281,7 +281,10 @@ def run_ours(opt, w):
     two_stage = bool(model.two_stage and _lib.lib.dadmm_unfolded_uses_factor(0, _lib.ALGOS[opt.algo], B_loc, w["P"], w["n"], w["m"]))
     with torch.no_grad():
         model.seq_hyp.param.copy_(param)
-    optim = torch.optim.Adam(model.parameters(), lr=1e-4)
+    use_graph = bool(opt.cuda_graph) and world == 1 and not opt.inference
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=use_graph)
+    if use_graph:
+        model.check_finite = "deferred"       # no host read inside the captured step (dadmm_b200/graphs.py)
 
     def step(b, label, graph_arg=None):
         g = graphs if graph_arg is None else graph_arg
@@ -295,8 +298,9 @@ def run_ours(opt, w):
                 D.allreduce_sum_([loss_val])
             return loss_val
         Y, _ = model(b, g)
-        # the reference's call, NaN guards included (they cost one host read of a few bytes here: gnn_dlasso_utils.compute_loss)
-        loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, global_batch=B_glob)
+        # the reference's call, NaN guards included (they cost one host read of a few bytes here: gnn_dlasso_utils.compute_loss);
+        # under CUDA-graph capture the guards are the sticky device flags read after the run (model.nonfinite_seen())
+        loss_mean, loss_final = gnn_dlasso_utils.compute_loss(Y, label, global_batch=B_glob, check_finite=not use_graph)
         optim.zero_grad(set_to_none=True)
         loss_final.backward()
         loss_val = loss_final.detach().clone()
@@ -318,6 +322,18 @@ def run_ours(opt, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    eager_step, launches_per_graph = step, None
+    if use_graph:
+        from dadmm_b200.graphs import GraphedStep
+        n_before = _lib.launch_count()
+        graphed = GraphedStep(lambda b, label: eager_step(b, label), [b_dev, label_dev], warmup=3)
+        launches_per_graph = (_lib.launch_count() - n_before) // 4          # three warm-up calls + the captured one
+
+        def step(b, label, graph_arg=None):                     # noqa: F811 -- the timed loops below replay the graph
+            if graph_arg is not None:
+                return eager_step(b, label, graph_arg)
+            return graphed(b, label).clone()          # the captured output buffer is overwritten by the next replay
+
     # ---- device-resident timing (value) ------------------------------------------------------------------
     for _ in range(max(opt.warmup, 3)):
         step(b_dev, label_dev)
@@ -334,7 +350,7 @@ def run_ours(opt, w):
         loss = step(b_dev, label_dev)
     e1.record()
     barrier()
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() - n0 if not use_graph else launches_per_graph * opt.steps
     clocks = sampler.stop()
     t_dev = max_over_ranks(e0.elapsed_time(e1) / 1e3) / opt.steps
     loss_val = float(loss.detach())
@@ -382,7 +398,7 @@ def run_ours(opt, w):
     t_e2e = max_over_ranks((time.perf_counter() - t0)) / n_e2e
     # the same loop with fresh graphs every step (the fixed-list loops above hit BatchGraph's cache: ingestion amortised)
     t_e2e_fresh = None
-    if opt.workload != "cfg1":            # configs[0] is the one-shared-graph driver (unfolded_train_new.py:56)
+    if opt.workload != "cfg1" and not use_graph:            # configs[0] is the one-shared-graph driver (unfolded_train_new.py:56)
         e2e_loop(2, fresh_graphs=True)
         barrier()
         t0 = time.perf_counter()
@@ -396,7 +412,7 @@ def run_ours(opt, w):
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    step(b_dev, label_dev)
+    eager_step(b_dev, label_dev)
     p1.record()
     torch.cuda.synchronize()
     prof = _lib.profile_read()
@@ -420,7 +436,9 @@ def run_ours(opt, w):
                                 "forward K iters + compute_loss (NaN guards on, as the reference drivers call it) + loss_final.backward + grad allreduce + Adam"),
                        "graphs": "one fixed list of per-problem graphs reused every step (ingestion amortised by BatchGraph's cache); "
                                  "e2e.fresh_graphs times the loop with new graphs drawn and ingested on the device every step",
-                       "launch_chain": "classic" if opt.no_pdl else "programmatic dependent launch",
+                       "launch_chain": ("classic" if opt.no_pdl else "programmatic dependent launch") +
+                                       (", whole step replayed as ONE CUDA graph (non-finite flags read after the run: "
+                                        f"{'hit' if model.nonfinite_seen() else 'clean'})" if use_graph else ""),
                        "operator_split": "cached with the operator (a constructor-time constant, like the reference's AtA)"},
             "clocks": clocks,
             "e2e": {"value": w["K"] * B_glob / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e, "steps": n_e2e,
@@ -548,6 +566,9 @@ def main():
                     help="contraction kernel; 'fast' is the FLAGGED reduced-precision mode (fp16 operands, 1e-2 class) and is "
                          "never the default: the headline number is measured in fp32-parity mode")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the whole training step (forward, loss, backward, Adam) into one CUDA graph and time its replays "
+                         "(host-bound shapes: --workload cfg1); single GPU")
     ap.add_argument("--inference", action="store_true",
                     help="time the no_grad forward sweep + compute_loss instead of a training step (BASELINE configs[4]: --workload cfg5)")
     ap.add_argument("--batch", type=int, default=None,

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) contract_simt_kernel(co
     constexpr int GM = TM / 4, GN = TN / 4;  // groups of 4 consecutive outputs per thread
     __shared__ __align__(32) T As[2][BK][BM + PAD];
     __shared__ __align__(32) T Bs[2][BK][BN + PAD];
+    pdl_wait();            // chain kernel (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int tid = threadIdx.x;
     const int tx = tid % (BM / TM), ty = tid / (BM / TM);
     const int i0 = blockIdx.x * BM, b0 = blockIdx.y * BN, ag = blockIdx.z;
@@ -198,8 +200,8 @@ template <typename T, typename C, int WMODE, int XMODE>
 int launch_contract_simt_cfg(const GemmParams<T>& p, cudaStream_t s) {
     dim3 grid(ceil_div(p.M, C::BM), ceil_div(p.B, C::BN), p.P);
     ProfScope prof(PROF_CONTRACT_SIMT, s);
-    contract_simt_kernel<T, C::BM, C::BN, C::BK, C::TM, C::TN, WMODE, XMODE>
-        <<<grid, (C::BM / C::TM) * (C::BN / C::TN), 0, s>>>(p);
+    DADMM_CUDA(launch_chain(contract_simt_kernel<T, C::BM, C::BN, C::BK, C::TM, C::TN, WMODE, XMODE>, grid,
+                            dim3((C::BM / C::TM) * (C::BN / C::TN)), 0, s, p));
     DADMM_LAUNCHED();
     return 0;
 }

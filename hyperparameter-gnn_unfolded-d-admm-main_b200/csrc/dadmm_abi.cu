@@ -16,6 +16,7 @@
 #include "unfolded.cuh"
 #include "unfolded_lean.cuh"
 #include "unfolded_pipe.cuh"
+#include "gcn.cuh"
 
 namespace dadmm {
 thread_local char g_err[512] = "";
@@ -322,7 +323,7 @@ static bool lean_gen2() {
 static int lean_minb(bool fwd) {
     static const int f = [] { const char* e = getenv("DADMM_LEAN_MINB_FWD"); return e ? atoi(e) : 0; }();
     static const int b = [] { const char* e = getenv("DADMM_LEAN_MINB_BWD"); return e ? atoi(e) : 0; }();
-    return fwd ? (f ? f : 5) : (b ? b : 4);
+    return fwd ? (f ? f : 4) : (b ? b : 4);      // forward: 4 CTAs x 64 registers, no spills (23.7 ms per step against 25.8 at 5 x 48)
 }
 template <typename K, typename Prm>
 static int launch_level(K kernel, int grid, int threads, size_t smem, cudaStream_t s, const Prm& p) {
@@ -341,8 +342,10 @@ static int sm_count() {
     return n;
 }
 // forward level as a persistent TMA pipeline (unfolded_pipe.cuh); DADMM_FWD_PIPE=0 keeps the occupancy-driven kernels
+// (measured with one 512-byte bulk copy per tile row: 1.34 ms per level against 0.95 -- the copy engine, not HBM, paces
+// 150 small copies per tile; off by default, DADMM_FWD_PIPE=1 selects it)
 static bool fwd_pipe_enabled() {
-    static const bool on = [] { const char* e = getenv("DADMM_FWD_PIPE"); return !(e && atoi(e) == 0); }();
+    static const bool on = [] { const char* e = getenv("DADMM_FWD_PIPE"); return e && atoi(e) == 1; }();
     return on;
 }
 // problems per tile of the pipelined kernel: as many as keep the tile at or below 64 rows, dividing the batch
@@ -419,10 +422,36 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                         p.sq_part = sq_part;
                         if (sums_grid) *sums_grid = grid;
                     }
-                    if (int e = ncons == 8    ? launch_level(pipe::level_fwd_pipe_kernel<8>, grid, 9 * 32, psmem, s, p)
-                                : ncons == 12 ? launch_level(pipe::level_fwd_pipe_kernel<12>, grid, 13 * 32, psmem, s, p)
-                                              : launch_level(pipe::level_fwd_pipe_kernel<16>, grid, 17 * 32, psmem, s, p))
-                        return e;
+                    // tiled tensor maps of the three input tensors ([B*P, n] fp32, box [tile rows] x [128 unknowns])
+                    static const bool tmap = [] { const char* e = getenv("DADMM_PIPE_TMAP"); return !(e && atoi(e) == 0); }();
+                    CUtensorMap maps[3];
+                    memset(maps, 0, sizeof(maps));
+                    bool use_tmap = tmap && tb * P <= 256 && tc::encode_fn() != nullptr;
+                    if (use_tmap) {
+                        const void* src[3] = {y, a, U_in};
+                        for (int q = 0; q < 3 && use_tmap; ++q) {
+                            cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)B * P}, strides[1] = {(cuuint64_t)n * 4};
+                            cuuint32_t box[2] = {128, (cuuint32_t)(tb * P)}, es[2] = {1, 1};
+                            use_tmap = tc::encode_fn()(&maps[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)src[q], dims, strides, box, es,
+                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                        }
+                    }
+#define DADMM_LAUNCH_PIPE(NC, TM)                                                                                         \
+    {                                                                                                                      \
+        if (int e = allow_smem(pipe::level_fwd_pipe_kernel<NC, TM>, psmem)) return e;                                     \
+        DADMM_CUDA(launch_chain(pipe::level_fwd_pipe_kernel<NC, TM>, dim3(grid), dim3((NC + 1) * 32), psmem, s, p, maps[0], maps[1], maps[2])); \
+    }
+                    if (use_tmap) {
+                        if (ncons == 8) DADMM_LAUNCH_PIPE(8, true)
+                        else if (ncons == 12) DADMM_LAUNCH_PIPE(12, true)
+                        else DADMM_LAUNCH_PIPE(16, true)
+                    } else {
+                        if (ncons == 8) DADMM_LAUNCH_PIPE(8, false)
+                        else if (ncons == 12) DADMM_LAUNCH_PIPE(12, false)
+                        else DADMM_LAUNCH_PIPE(16, false)
+                    }
+#undef DADMM_LAUNCH_PIPE
                     DADMM_LAUNCHED();
                     return 0;
                 }
@@ -591,10 +620,11 @@ static int fused_contract(const FusedWs& f, char* w8, char* xsp, int B, int P, i
     if (!f.two) return f16::launch(B, P, n, n, w8, xsp, out, (int64_t)P * n, accumulate, s, amax_out, sub, fast);
     char* tsp = xsp + f.xb;
     const unsigned* rhs_amax = (const unsigned*)(tsp + 48);       // spare scalar slot of the t split header
-    // partial-sum lengths: 64 k in the long first stage (1.5e-7 rel-L2), 128 k in the short, epilogue-heavy second
-    // stage (3.7e-7) -- composite 4.0e-7, the exact-FMA kernel's error for the same n; the opposite assignment is
-    // equally accurate and 0.09 ms per contraction slower (B200, cfg4)
-    if (int e = f16::launch(B, P, m, n, w8, xsp, nullptr, (int64_t)P * m, 0, s, nullptr, rhs, fast, tsp, 1, rhs ? rhs_amax : nullptr))
+    // partial-sum lengths: 128 k in both stages (3.7e-7 rel-L2 each, composite 5.2e-7 against 4.1e-7 for the exact-FMA
+    // kernel at n = 1024 and a 1e-5 tolerance).  Round 1 ran the first stage with 64-k partial sums (composite 4.0e-7); the
+    // 128 KB TMEM drain per partial sum paces that stage, and halving the number of drains takes it from 0.33 to 0.29 ms
+    // (16.0 -> 14.5 ms per training step at cfg4; DADMM_F16_KBC overrides the length for both stages)
+    if (int e = f16::launch(B, P, m, n, w8, xsp, nullptr, (int64_t)P * m, 0, s, nullptr, rhs, fast, tsp, 2, rhs ? rhs_amax : nullptr))
         return e;
     return f16::launch(B, P, n, m, w8 + f.w1, tsp, out, (int64_t)P * n, accumulate, s, amax_out, rhs ? nullptr : sub, fast, nullptr, 2);
 }
@@ -1043,6 +1073,57 @@ int dadmm_loss_bwd(int dtype, int K, int B, int P, int n, const void* Y, const v
             DADMM_FAIL(-1, "loss_bwd: unknown dtype %d", dtype);
         }
     }
+    return 0;
+}
+
+static int gcn_check(int B, int P, int C) {
+    if (B <= 0 || P <= 0 || C <= 0) DADMM_FAIL(-1, "gcn_epilogue: bad dims");
+    if (P > gcn::kMaxP) DADMM_FAIL(-2, "gcn_epilogue: P=%d above the %d agents one tile holds", P, gcn::kMaxP);
+    return 0;
+}
+
+int dadmm_gcn_partial_rows(int B, int C) { return B > 0 && C > 0 ? ceil_div(B, gcn::problems_per_cta(B, C)) : 0; }
+
+int dadmm_gcn_epilogue_fwd(int B, int P, int C, const void* H, const void* adj, const void* bias, const void* bn_w,
+                           const void* bn_b, const void* run_mean, const void* run_var, int training, double eps,
+                           double slope, const void* mask, void* out, void* act, void* mean, void* var,
+                           dadmm_stream_t stream) {
+    if (int e = gcn_check(B, P, C)) return e;
+    if (!H || !adj || !bias || !bn_w || !bn_b || !out || !act) DADMM_FAIL(-1, "gcn_epilogue_fwd: null pointer");
+    if (training ? (!mean || !var) : (!run_mean || !run_var)) DADMM_FAIL(-1, "gcn_epilogue_fwd: statistics pointers missing");
+    gcn::Params p{};
+    p.B = B; p.P = P; p.C = C; p.G = gcn::problems_per_cta(B, C);
+    p.H = (const float*)H; p.adj = (const float*)adj; p.bias = (const float*)bias; p.bn_w = (const float*)bn_w;
+    p.bn_b = (const float*)bn_b; p.run_mean = (const float*)run_mean; p.run_var = (const float*)run_var;
+    p.mask = (const float*)mask; p.eps = (float)eps; p.slope = (float)slope; p.training = training ? 1 : 0;
+    p.out = (float*)out; p.act = (float*)act; p.mean = (float*)mean; p.var = (float*)var;
+    const size_t smem = gcn::smem_bytes(P);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = allow_smem(gcn::epilogue_fwd_kernel, smem)) return e;
+    gcn::epilogue_fwd_kernel<<<dim3(ceil_div(C, gcn::kThreads), ceil_div(B, p.G)), gcn::kThreads, smem, s>>>(p);
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+int dadmm_gcn_epilogue_bwd(int B, int P, int C, const void* gout, const void* adj, const void* bn_w, const void* run_mean,
+                           const void* run_var, int training, double eps, double slope, const void* mask,
+                           const void* act, const void* mean, const void* var, void* gH, void* partials,
+                           dadmm_stream_t stream) {
+    if (int e = gcn_check(B, P, C)) return e;
+    if (!gout || !adj || !bn_w || !act || !gH || !partials) DADMM_FAIL(-1, "gcn_epilogue_bwd: null pointer");
+    if (training ? (!mean || !var) : (!run_mean || !run_var)) DADMM_FAIL(-1, "gcn_epilogue_bwd: statistics pointers missing");
+    gcn::Params p{};
+    p.B = B; p.P = P; p.C = C; p.G = gcn::problems_per_cta(B, C);
+    p.gout = (const float*)gout; p.adj = (const float*)adj; p.bn_w = (const float*)bn_w;
+    p.run_mean = (const float*)run_mean; p.run_var = (const float*)run_var; p.mask = (const float*)mask;
+    p.eps = (float)eps; p.slope = (float)slope; p.training = training ? 1 : 0;
+    p.act = (float*)act; p.mean = (float*)mean; p.var = (float*)var;
+    p.gH = (float*)gH; p.partials = (float*)partials;
+    const size_t smem = gcn::smem_bytes(P);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = allow_smem(gcn::epilogue_bwd_kernel, smem)) return e;
+    gcn::epilogue_bwd_kernel<<<dim3(ceil_div(C, gcn::kThreads), ceil_div(B, p.G)), gcn::kThreads, smem, s>>>(p);
+    DADMM_LAUNCHED();
     return 0;
 }
 

@@ -14,7 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
@@ -93,6 +93,9 @@ def _load():
         "dadmm_loss_bwd": (i32, [i32, i32, i32, i32, i32, vp, vp, C.POINTER(dbl), vp, vp]),
         "dadmm_loss_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
         "dadmm_loss_from_sums": (i32, [i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp]),
+        "dadmm_gcn_epilogue_fwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
+        "dadmm_gcn_epilogue_bwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, vp, vp, vp, vp]),
+        "dadmm_gcn_partial_rows": (i32, [i32, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

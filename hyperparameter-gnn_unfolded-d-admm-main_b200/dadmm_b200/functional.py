@@ -92,6 +92,23 @@ def contract(W: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = Non
     return out
 
 
+def observe(A: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """b[i,p,:] = A[p] @ y[i,:] for every agent in one launch (``set_Data``, reference gnn_data.py:13-14: a Python loop of P
+    matmuls).  A [P,m,n], y [N,n] -> [N,P,m]; the shared input enters the contraction with a zero agent stride."""
+    dev = require_cuda(A, y, out)
+    A, y = A.contiguous(), y.contiguous()
+    P, m, n = A.shape
+    N = y.shape[0]
+    same_dtype("observe", y, A=A, out=out)
+    if out is None:
+        out = torch.empty((N, P, m), dtype=y.dtype, device=dev)
+    assert out.shape == (N, P, m) and out.is_contiguous() and y.shape == (N, n)
+    with device_guard(dev):
+        check(lib.dadmm_contract(dtype_code(y), _lib.ALGO_SIMT, N, P, m, n, ptr(A), m * n, n, 1, ptr(y), n, 0, 1,
+                                 ptr(out), P * m, m, 1, 0, None, 0, stream_ptr(dev)), "dadmm_contract(observe)")
+    return out
+
+
 def atx(A: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """``compute_Atx`` (unfolded_DLASSO.py:120-124): Atx[:,p] = A[0,p].T @ x[:,p].
     A [1,P,m,n]; x [Bx,P,m,c] -> [Bx,P,n,c]."""
@@ -387,6 +404,63 @@ class Unfolded(torch.autograd.Function):
             if ent is not None:
                 ent[1] = True
         return (ghyp,) + (None,) * 13
+
+
+class GCNEpilogue(torch.autograd.Function):
+    """Everything a graph-convolution layer of the model-#3 hypernetwork does after its dense product, for the whole
+    batch in one kernel each way (``dadmm_gcn_epilogue_fwd`` / ``_bwd``; reference gnn_dlasso_models_progressive.py:37-72,
+    there a Python loop over the samples):
+
+        Z = A_hat_b H_b + bias;  A = leaky_relu(Z);  BatchNorm over the P nodes of problem b;  out = BN(A) * mask
+
+    H [B,P,C] (= ``conv.lin(x)``), adj [B,P,P], mask [B,P,C] or None (dropout keep mask already divided by 1-p).  Returns
+    (out, mean, var): the per-problem batch statistics ([B,C], biased variance; training mode only, else None) feed the
+    running-statistics update and carry no gradient.  Gradients: H, conv bias, BN weight and bias."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, H, adj, bias, bn_w, bn_b, run_mean, run_var, training, eps, slope, mask):
+        dev = require_cuda(H, adj, bias, bn_w, bn_b, mask)
+        if H.dtype != torch.float32:
+            raise _lib.DadmmError("GCNEpilogue computes in float32")
+        same_dtype("GCNEpilogue", H, adj=adj, bias=bias, bn_w=bn_w, bn_b=bn_b, mask=mask, run_mean=run_mean, run_var=run_var)
+        B, P, Cc = H.shape
+        H, adj = H.contiguous(), adj.contiguous()
+        mask = mask.contiguous() if mask is not None else None
+        out, act = torch.empty_like(H), torch.empty_like(H)
+        mean = torch.empty((B, Cc), dtype=H.dtype, device=dev) if training else None
+        var = torch.empty((B, Cc), dtype=H.dtype, device=dev) if training else None
+        with device_guard(dev):
+            check(lib.dadmm_gcn_epilogue_fwd(B, P, Cc, ptr(H), ptr(adj), ptr(bias), ptr(bn_w), ptr(bn_b), ptr(run_mean), ptr(run_var),
+                                             int(bool(training)), float(eps), float(slope), ptr(mask), ptr(out), ptr(act), ptr(mean),
+                                             ptr(var), stream_ptr(dev)), "dadmm_gcn_epilogue_fwd")
+        # training mode never reads the running statistics (and the caller updates them in place right after this call)
+        ctx.save_for_backward(adj, bn_w, None if training else run_mean, None if training else run_var, mask, act, mean, var)
+        ctx.cfg = (bool(training), float(eps), float(slope))
+        if training:
+            ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)
+        return out, mean, var
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout, _gm, _gv):
+        adj, bn_w, run_mean, run_var, mask, act, mean, var = ctx.saved_tensors
+        if gout is None:
+            return (None,) * 11
+        training, eps, slope = ctx.cfg
+        B, P, Cc = act.shape
+        dev = act.device
+        gout = gout.contiguous().to(act.dtype)
+        gH = torch.empty_like(act)
+        rows = int(lib.dadmm_gcn_partial_rows(B, Cc))
+        part = torch.empty((rows, 3, Cc), dtype=act.dtype, device=dev)
+        with device_guard(dev):
+            check(lib.dadmm_gcn_epilogue_bwd(B, P, Cc, ptr(gout), ptr(adj), ptr(bn_w), ptr(run_mean), ptr(run_var), int(training),
+                                             eps, slope, ptr(mask), ptr(act), ptr(mean), ptr(var), ptr(gH), ptr(part), stream_ptr(dev)),
+                  "dadmm_gcn_epilogue_bwd")
+        sums = part.sum(dim=0)                  # rows of per-CTA partial sums -> (d bn_w, d bn_b, d bias)
+        return gH, None, sums[2], sums[0], sums[1], None, None, None, None, None, None
 
 
 def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[int] = None, handle=None) -> torch.Tensor:

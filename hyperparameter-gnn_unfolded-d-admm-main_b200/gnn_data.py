@@ -18,11 +18,18 @@ class GNN_Data(Dataset):
 
 def make_problem(A, data_len):
     """Labels y = 2*N(0,1)*Bernoulli(0.25) and noiseless observations b_p = A_p y (reference :6-14:
-    the sigma-scaled noise drawn at :12 is overwritten at :13-14, so it only advances the RNG)."""
+    the sigma-scaled noise drawn at :12 is overwritten at :13-14, so it only advances the RNG).
+
+    With ``A`` on a CUDA device the P per-agent products of the reference's loop (:13-14) are ONE launch of the library's
+    contraction (every agent reads the same y: a zero agent stride, no [N,P,n] copy); on the CPU the loop stays as it is."""
     device = A.device
     _, P, m, n = A.shape
     y = 2 * torch.randn(data_len, n, 1, device=device) * (torch.rand(data_len, n, 1, device=device) <= 0.25)
     b = torch.randn(data_len, P, m, 1, device=device)          # keeps the reference's RNG stream position
+    if A.is_cuda:
+        from dadmm_b200 import functional as DF
+        DF.observe(A[0], y.squeeze(-1), out=b.squeeze(-1))
+        return b, y
     for p in range(P):
         b[:, p] = torch.matmul(A[0, p], y)
     return b, y

@@ -131,13 +131,40 @@ class GNNHypernetwork3(nn.Module):
                 bn.running_var.unsqueeze(0).addmm_(w, var[:, 0], beta=keep, alpha=Pn / max(Pn - 1, 1))
         return out
 
+    def _layer_fused(self, conv, bn, x, adj_hat, drop):
+        """One layer through ``DF.GCNEpilogue``: dense product by cuBLAS, then ONE kernel for adjacency mix, bias, LeakyReLU,
+        the per-graph BatchNorm and the dropout mask (CUDA, float32, P <= 64)."""
+        Bn, Pn, _ = x.shape
+        training_bn = bn.training or not bn.track_running_stats
+        mask = None
+        if drop and self.dropout.training and self.dropout.p > 0:
+            keep = 1.0 - self.dropout.p
+            mask = torch.empty((Bn, Pn, conv.lin.out_features), dtype=x.dtype, device=x.device).bernoulli_(keep).div_(keep)
+        out, mean, var = DF.GCNEpilogue.apply(conv.lin(x), adj_hat, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                              training_bn, bn.eps, 0.01, mask)
+        if training_bn and bn.track_running_stats:
+            with torch.no_grad():          # the B sequential running-stat updates of the reference's per-sample calls, in closed form
+                mom = 0.1 if bn.momentum is None else bn.momentum
+                w = _ema_weights(Bn, mom, x.device, x.dtype)
+                keep_r = (1.0 - mom) ** Bn
+                bn.running_mean.unsqueeze(0).addmm_(w, mean, beta=keep_r)
+                bn.running_var.unsqueeze(0).addmm_(w, var, beta=keep_r, alpha=Pn / max(Pn - 1, 1))
+        return out
+
     def forward(self, x, graph_list, adj_hat=None):
         """x [B,P,m,1] -> [B, P*4*hidden]  (reference :37-72)."""
         batch_size = x.shape[0]
         x = x.squeeze(-1)
         if adj_hat is None:
             adj_hat = normalized_adjacency(graph_list, self.P, x.device, x.dtype)
+        fused = (getattr(self, "fused", True) and x.is_cuda and x.dtype == torch.float32 and self.P <= 64
+                 and not torch.is_autocast_enabled())
         for i in range(1, 6):
+            if fused:
+                x = self._layer_fused(getattr(self, f"conv{i}"), getattr(self, f"bn{i}"), x, adj_hat, drop=(i < 5))
+                if i == 5:
+                    x = self.norm(x)
+                continue
             x = F.leaky_relu(getattr(self, f"conv{i}")(x, adj_hat))
             x = self._per_sample_bn(getattr(self, f"bn{i}"), x)
             x = self.dropout(x) if i < 5 else self.norm(x)
@@ -237,14 +264,35 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
             d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
         else:
             y0, U0, d0 = (t.to(device=device, dtype=W.dtype).reshape(B, self.P, self.n, 1) for t in noise)
-        flags = torch.zeros(max(K, 1), dtype=torch.int32, device=device) if self.check_finite else None
+        deferred = self.check_finite == "deferred"        # sticky flags, read by nonfinite_seen() only (dadmm_b200/graphs.py)
+        if deferred:
+            flags = self._sticky_flags(device, max(K, 1))
+        else:
+            flags = torch.zeros(max(K, 1), dtype=torch.int32, device=device) if self.check_finite else None
         out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, flags, guarded=False)
-        if flags is not None:
+        if flags is not None and not deferred:
             if bool(flags.any()):
                 out = self._iterate(K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, None, guarded=True)
             else:
                 out[0]._dadmm_finite = out[0]._version      # no kernel saw a non-finite value (compute_loss skips its scan)
         return out
+
+    def _sticky_flags(self, device, K):
+        buf = self.__dict__.get("_flag_buf")
+        if buf is None or buf.device != device or buf.numel() < K:
+            buf = torch.zeros(max(K, self.K), dtype=torch.int32, device=device)
+            self.__dict__["_flag_buf"] = buf
+        return buf
+
+    def nonfinite_seen(self, reset=True):
+        """``check_finite = "deferred"``: has any forward pass since the last call met a non-finite value?  (one host read)"""
+        buf = self.__dict__.get("_flag_buf")
+        if buf is None:
+            return False
+        hit = bool(buf.any())
+        if reset and hit:
+            buf.zero_()
+        return hit
 
     def _iterate(self, K, W, Wt, Atb, y0, U0, d0, graph, graph_list, adj_hat, flags, guarded):
         bad = lambda t: bool(torch.isnan(t).any() or torch.isinf(t).any())

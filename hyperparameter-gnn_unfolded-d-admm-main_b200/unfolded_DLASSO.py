@@ -100,7 +100,10 @@ class DLASSO_unfolded(nn.Module):
         self.args = args
         # knobs of the B200 path
         self.contract_algo = "auto"      # "auto" | "simt" | "tc" (tcgen05 3xTF32)
-        self.check_finite = True         # one device flag read per forward (reference: 4 host syncs / iteration)
+        # True: one device flag read per forward (reference: 4 host syncs / iteration) and the reference's reset / skip
+        # semantics on a hit; "deferred": the flags accumulate in a sticky device buffer that only nonfinite_seen() reads
+        # (no host sync in forward: what CUDA-graph capture of a whole step needs, dadmm_b200/graphs.py); False: no flags
+        self.check_finite = True
         self.two_stage = True            # offer AtA = A^T A to the library as a factor pair (used where 4mn << 2n^2)
         self._ops = {}                   # device -> (A, AtA [P,n,n], AtA^T [P,n,n])
 
@@ -155,7 +158,11 @@ class DLASSO_unfolded(nn.Module):
     def _run(self, table, W, Wt, Atb, y0, U0, d0, graph, K, b=None):
         hyp = table.expand(K, self.P, 4).contiguous().to(W.dtype)
         clamps = [DF.clamps_model1(k) for k in range(K)]
-        flags = torch.zeros(K, dtype=torch.int32, device=W.device) if self.check_finite else None
+        deferred = self.check_finite == "deferred"
+        if deferred:
+            flags = self._sticky_flags(W.device, K)
+        else:
+            flags = torch.zeros(K, dtype=torch.int32, device=W.device) if self.check_finite else None
         handle = DF.FusedLossHandle()
         factor = factor_t = None
         if self.two_stage and W.dtype == torch.float32:
@@ -165,16 +172,35 @@ class DLASSO_unfolded(nn.Module):
             factor = (A[0], At, rhs)                     # forward: residual A^T (A y - b) = AtA y - Atb
         Y = DF.Unfolded.apply(hyp, W, Wt, Atb, y0.squeeze(-1), U0.squeeze(-1), d0.squeeze(-1), graph, clamps,
                               self.contract_algo, flags, handle, factor, factor_t)
-        if flags is not None and bool(flags.any()):
+        if flags is not None and not deferred and bool(flags.any()):
             # non-finite values seen: redo the batch on the guarded path, which reproduces the reference's
             # reset / skip semantics (:55-61, :84-86, :102-104) iteration by iteration
             if Atb is None:
                 Atb = self._atb(self._operators(W.device)[3], b, W.dtype)
             return self._run_guarded(hyp, W, Wt, Atb, y0, U0, d0, graph, K)
         Y._dadmm_handle = handle
-        if flags is not None:
+        if flags is not None and not deferred:
             Y._dadmm_finite = Y._version      # no kernel saw a non-finite value => Y is finite (compute_loss skips its scan)
         return Y
+
+    def _sticky_flags(self, device, K):
+        buf = self.__dict__.get("_flag_buf")
+        if buf is None or buf.device != device or buf.numel() < K:
+            buf = torch.zeros(max(K, self.K), dtype=torch.int32, device=device)
+            self.__dict__["_flag_buf"] = buf
+        return buf
+
+    def nonfinite_seen(self, reset=True):
+        """``check_finite = "deferred"``: has any forward pass since the last call met a non-finite value?  (One host read;
+        the kernels only ever OR bits into the buffer.)  Such a pass ran the plain recurrence on non-finite data -- rerun
+        the batch with ``check_finite = True`` for the reference's reset / skip semantics (:55-61, :84-86, :102-104)."""
+        buf = self.__dict__.get("_flag_buf")
+        if buf is None:
+            return False
+        hit = bool(buf.any())
+        if reset and hit:
+            buf.zero_()
+        return hit
 
     def _run_guarded(self, hyp, W, Wt, Atb, y0, U0, d0, graph, K):
         bad = lambda t: bool(torch.isnan(t).any() or torch.isinf(t).any())

@@ -17,6 +17,8 @@
  *   dadmm_unfolded_fwd  <- the whole `for k in range(K)` loop, unfolded_DLASSO.py:53-107
  *   dadmm_unfolded_bwd  <- loss.backward() through that loop (unfolded_train_new.py:79)
  *   dadmm_loss_fwd/bwd  <- gnn_dlasso_utils.py:27-88 (compute_loss) and its backward
+ *   dadmm_gcn_epilogue_fwd/bwd <- gnn_dlasso_models_progressive.py:37-72 (the per-sample GCN layer loop of the
+ *                          hypernetwork: adjacency mix, bias, LeakyReLU, per-graph BatchNorm, dropout mask)
  *
  * Conventions: all data pointers are DEVICE pointers to contiguous arrays of `dtype`
  * (DADMM_F32 / DADMM_F64) unless a stride is given; state tensors are [B,P,n] with n fastest
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 5
+#define DADMM_ABI_VERSION 6
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -246,6 +248,24 @@ size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n);
 int dadmm_loss_from_sums(int dtype, int k0, int k1, int B, int P, int n, int64_t B_norm, const void* agent_sum,
                          const double* sumsq, const void* label, void* losses, void* ws, size_t ws_bytes,
                          dadmm_stream_t stream);
+
+/* Per-problem epilogue of one graph-convolution layer of the model-#3 hypernetwork (fp32 only) -- replaces, for the whole
+ * batch at once, what gnn_dlasso_models_progressive.py:37-72 does sample by sample after the dense product H = x W^T:
+ *     Z = A_hat_b H_b + bias;  A = leaky_relu(Z, slope);  BatchNorm over the P nodes of problem b (training: batch
+ *     statistics of that one graph; otherwise the running statistics);  out = BN(A) * mask
+ * H, out, act, mask: [B*P, C] row-major; adj: [B,P,P]; bias, bn_w, bn_b, run_mean, run_var: [C]; mean, var (biased):
+ * [B,C], written in training mode only; mask (may be NULL) already carries the 1/(1-p) scale of dropout.  P <= 64.
+ * The backward returns gH = d loss / d H and one row of partial sums per CTA, partials[nblk][3][C] = (d bn_w, d bn_b,
+ * d bias), nblk = dadmm_gcn_partial_rows(B, C); the caller sums the rows. */
+int dadmm_gcn_epilogue_fwd(int B, int P, int C, const void* H, const void* adj, const void* bias, const void* bn_w,
+                           const void* bn_b, const void* run_mean, const void* run_var, int training, double eps,
+                           double slope, const void* mask, void* out, void* act, void* mean, void* var,
+                           dadmm_stream_t stream);
+int dadmm_gcn_epilogue_bwd(int B, int P, int C, const void* gout, const void* adj, const void* bn_w, const void* run_mean,
+                           const void* run_var, int training, double eps, double slope, const void* mask,
+                           const void* act, const void* mean, const void* var, void* gH, void* partials,
+                           dadmm_stream_t stream);
+int dadmm_gcn_partial_rows(int B, int C);
 
 #ifdef __cplusplus
 }
