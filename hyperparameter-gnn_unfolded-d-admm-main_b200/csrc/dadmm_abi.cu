@@ -22,6 +22,7 @@ namespace dadmm {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_pdl{-1};
+std::atomic<int> g_exact_order{-1};      // consensus accumulation order of the lean forward level (dadmm_set_consensus_order)
 
 // ------------------------------------------------------------------------------------------
 // per-kind kernel timing
@@ -312,6 +313,18 @@ static bool level_ten_warps(int rows) {
     return (rows % 8) != 0 && (rows % 10) == 0;
 }
 
+// 1: the lean forward level accumulates 2L y in the reference's event order (bit-identical delta, twice the gathers);
+// 0 (default): each neighbour difference once, doubled.  DADMM_EXACT_ORDER=1 / dadmm_set_consensus_order(1) select the former.
+static bool exact_order() {
+    int v = g_exact_order.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DADMM_EXACT_ORDER");
+        v = (e && atoi(e) == 1) ? 1 : 0;
+        g_exact_order.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+
 // second-generation lean level kernels (unfolded_lean.cuh: packed fp32 arithmetic, byte-offset lists); DADMM_LEVEL_GEN=1
 // keeps the first generation (A/B measurements)
 static bool lean_gen2() {
@@ -320,10 +333,12 @@ static bool lean_gen2() {
 }
 
 // CTAs per SM the lean kernels' registers are budgeted for: DADMM_LEAN_MINB_FWD / _BWD override the defaults
-static int lean_minb(bool fwd) {
+// (forward, B200, cfg4, ms per training step in the forward levels: event-order gather 24.5 at 4 CTAs x 64 registers / 25.8
+// at 5 x 48 with spills; half-length gather 23.6 at 4 / 22.7 at 5 -- with half the gathers in flight the extra warps win)
+static int lean_minb(bool fwd, bool exact = false) {
     static const int f = [] { const char* e = getenv("DADMM_LEAN_MINB_FWD"); return e ? atoi(e) : 0; }();
     static const int b = [] { const char* e = getenv("DADMM_LEAN_MINB_BWD"); return e ? atoi(e) : 0; }();
-    return fwd ? (f ? f : 4) : (b ? b : 4);      // forward: 4 CTAs x 64 registers, no spills (23.7 ms per step against 25.8 at 5 x 48)
+    return fwd ? (f ? f : (exact ? 4 : 5)) : (b ? b : 4);
 }
 template <typename K, typename Prm>
 static int launch_level(K kernel, int grid, int threads, size_t smem, cudaStream_t s, const Prm& p) {
@@ -368,6 +383,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.sp = sp;
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr);
     p.lst_ptr = g->ev_ptr; p.lst_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
+    p.exact_order = 1;
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
     p.G = (T)cl_k->G; p.V = (T)cl_k->V;
     p.hasD = std::isfinite(cl_k->D) ? 1 : 0;
@@ -407,13 +423,25 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                 p.sq_part = sq_part;
                 if (sums_grid) *sums_grid = c.grid;
             }
-            if (lean && !p.first && fwd_pipe_enabled() && lean_gen2()) {
-                const int tb = pipe_tb(B, P);
-                const size_t psmem = pipe::fwd_smem_bytes(tb, P, std::max(g->max_events, 1));
-                if (psmem <= 227 * 1024) {
+            // kernels of unfolded_lean.cuh / unfolded_pipe.cuh: which one can serve this launch
+            const bool gen2 = lean && !p.first && lean_gen2();
+            const int pipe_tbv = pipe_tb(B, P);
+            const bool fast = gen2 && !exact_order();      // half-length consensus gather (lean::lap_half): plain adjacency lists
+            const int list_max = fast ? g->max_adj : g->max_events;
+            const bool can_pipe = gen2 && fwd_pipe_enabled() && pipe::fwd_smem_bytes(pipe_tbv, P, std::max(list_max, 1)) <= 227 * 1024;
+            const bool can_lean2 = gen2 && p.list_cap > 0;
+            if (fast && (can_pipe || can_lean2)) {
+                p.exact_order = 0;
+                p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx;
+                if (p.list_cap > 0) p.list_cap = std::max(list_max, 1);      // never larger than the event lists the tile was sized for
+            }
+            if (can_pipe) {
+                const int tb = pipe_tbv;
+                const size_t psmem = pipe::fwd_smem_bytes(tb, P, std::max(list_max, 1));
+                {
                     static const int ncons = [] { const char* e = getenv("DADMM_PIPE_WARPS"); return e ? atoi(e) : 16; }();
                     p.TB = tb;
-                    p.list_cap = std::max(g->max_events, 1);
+                    p.list_cap = std::max(list_max, 1);
                     p.csplit = 1;
                     const long long tiles = (long long)(B / tb) * (n / 128);
                     const int grid = (int)std::min<long long>(sm_count(), tiles);
@@ -456,8 +484,8 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                     return 0;
                 }
             }
-            if (lean && !p.first && p.list_cap > 0 && lean_gen2()) {
-                const int mb = lean_minb(true);
+            if (can_lean2) {
+                const int mb = lean_minb(true, p.exact_order != 0);
                 if (int e = mb == 3   ? launch_level(lean::level_fwd_lean_kernel<kStepThreads, 3>, c.grid, kStepThreads, smem, s, p)
                             : mb == 4 ? launch_level(lean::level_fwd_lean_kernel<kStepThreads, 4>, c.grid, kStepThreads, smem, s, p)
                                       : launch_level(lean::level_fwd_lean_kernel<kStepThreads, 5>, c.grid, kStepThreads, smem, s, p))
@@ -810,6 +838,12 @@ int dadmm_abi_version(void) { return DADMM_ABI_VERSION; }
 const char* dadmm_last_error(void) { return g_err; }
 int64_t dadmm_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int dadmm_set_consensus_order(int exact) {
+    const int prev = exact_order() ? 1 : 0;
+    g_exact_order.store(exact ? 1 : 0);
+    return prev;
+}
+
 int dadmm_set_pdl(int on) {
     const int prev = pdl_enabled() ? 1 : 0;
     g_pdl.store(on ? 1 : 0);
@@ -990,7 +1024,7 @@ int dadmm_unfolded_bwd(int dtype, int algo, int B, int P, int n, int K, const da
 
 size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n) {
     (void)dtype; (void)B; (void)P; (void)n;
-    return (size_t)K * 1024 * sizeof(double);
+    return (size_t)K * 1024 * sizeof(double) + (size_t)K * sizeof(int) + 16;      // per-CTA partial sums + the re-evaluation flags of dadmm_loss_from_sums
 }
 
 int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const void* Y, const void* label, void* losses,
@@ -1022,28 +1056,49 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
 }
 
 int dadmm_loss_from_sums(int dtype, int k0, int k1, int B, int P, int n, int64_t B_norm, const void* agent_sum,
-                         const double* sumsq, const void* label, void* losses, void* ws, size_t ws_bytes,
+                         const double* sumsq, const void* label, const void* Y, void* losses, void* ws, size_t ws_bytes,
                          dadmm_stream_t stream) {
     if (k0 < 0 || k1 <= k0 || B <= 0 || P <= 0 || n <= 0 || B_norm <= 0) DADMM_FAIL(-1, "loss_from_sums: bad dims");
     if (!agent_sum || !sumsq || !label || !losses || !ws) DADMM_FAIL(-1, "loss_from_sums: null pointer");
     if (ws_bytes < dadmm_loss_ws_bytes(dtype, k1, B, P, n)) DADMM_FAIL(-1, "loss_from_sums: workspace too small");
     const long long tot = (long long)B * n;
     const int nblk = (int)std::min<long long>(512, ceil_div64(tot, 2048));
+    const int Kn = k1 - k0;
     const double inv = 1.0 / ((double)P * (double)B_norm * (double)n);
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope prof(PROF_LOSS, s);
     double* part = (double*)ws;
+    int* need = Y ? (int*)((char*)ws + (size_t)k1 * 1024 * sizeof(double)) : nullptr;     // tail of the workspace (dadmm_loss_ws_bytes)
+    // where the sums cancel (need[k]), the iteration is evaluated again exactly from Y: same kernels as dadmm_loss_fwd, gated
+    // on the device flag -- no host round trip; an unflagged iteration costs its CTAs one load
+    const long long rows = (long long)B * P;
+    const int nblk_x = (int)std::min<long long>(1024, ceil_div64(rows, 8));
+    const bool v4 = (n % 4 == 0) && aligned_to(Y, 16) && aligned_to(label, 16);
     if (dtype == DADMM_F32) {
-        loss_sums_partial_kernel<float><<<dim3(nblk, k1 - k0), 256, 0, s>>>((const float*)agent_sum + (size_t)k0 * tot, (const float*)label, tot, part);
+        loss_sums_partial_kernel<float><<<dim3(nblk, Kn), 256, 0, s>>>((const float*)agent_sum + (size_t)k0 * tot, (const float*)label, tot, part);
         DADMM_LAUNCHED();
-        loss_sums_final_kernel<float><<<k1 - k0, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (float*)((char*)losses + (size_t)k0 * es));
+        loss_sums_final_kernel<float><<<Kn, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (float*)((char*)losses + (size_t)k0 * es), need);
         DADMM_LAUNCHED();
+        if (Y) {
+            const float* Yk = (const float*)Y + (size_t)k0 * rows * n;
+            if (v4) loss_partial_kernel<float, 4><<<dim3(nblk_x, Kn), 256, 0, s>>>(Yk, (const float*)label, B, P, n, part, need);
+            else loss_partial_kernel<float, 1><<<dim3(nblk_x, Kn), 256, 0, s>>>(Yk, (const float*)label, B, P, n, part, need);
+            DADMM_LAUNCHED();
+            loss_final_kernel<float><<<Kn, 256, 0, s>>>(part, nblk_x, Kn, inv, (float*)((char*)losses + (size_t)k0 * es), need);
+            DADMM_LAUNCHED();
+        }
     } else if (dtype == DADMM_F64) {
-        loss_sums_partial_kernel<double><<<dim3(nblk, k1 - k0), 256, 0, s>>>((const double*)agent_sum + (size_t)k0 * tot, (const double*)label, tot, part);
+        loss_sums_partial_kernel<double><<<dim3(nblk, Kn), 256, 0, s>>>((const double*)agent_sum + (size_t)k0 * tot, (const double*)label, tot, part);
         DADMM_LAUNCHED();
-        loss_sums_final_kernel<double><<<k1 - k0, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (double*)((char*)losses + (size_t)k0 * es));
+        loss_sums_final_kernel<double><<<Kn, 256, 0, s>>>(part, nblk, sumsq + k0, P, inv, (double*)((char*)losses + (size_t)k0 * es), need);
         DADMM_LAUNCHED();
+        if (Y) {
+            loss_partial_kernel<double, 1><<<dim3(nblk_x, Kn), 256, 0, s>>>((const double*)Y + (size_t)k0 * rows * n, (const double*)label, B, P, n, part, need);
+            DADMM_LAUNCHED();
+            loss_final_kernel<double><<<Kn, 256, 0, s>>>(part, nblk_x, Kn, inv, (double*)((char*)losses + (size_t)k0 * es), need);
+            DADMM_LAUNCHED();
+        }
     } else {
         DADMM_FAIL(-1, "loss_from_sums: unknown dtype %d", dtype);
     }

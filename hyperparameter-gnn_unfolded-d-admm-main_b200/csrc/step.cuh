@@ -407,10 +407,14 @@ __global__ void __launch_bounds__(256) reduce_hyp_sample_kernel(const T* __restr
 // ---------------------------------------------------------------------------------------------
 // grid = (nblk, K); one warp per (problem, agent) row, VEC-wide coalesced loads; fp32 within a row segment,
 // fp64 across rows.
+// `need` (optional, [gridDim.y]): launch-time-unknown selection of the iterations to evaluate -- a CTA whose iteration is
+// not flagged returns at once (dadmm_loss_from_sums re-evaluates from Y only where the sums cancelled)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) loss_partial_kernel(const T* __restrict__ Y, const T* __restrict__ label,
-                                                           int B, int P, int n, double* __restrict__ partial) {
+                                                           int B, int P, int n, double* __restrict__ partial,
+                                                           const int* __restrict__ need = nullptr) {
     const int k = blockIdx.y;
+    if (need && !need[k]) return;
     const long long rows = (long long)B * P;
     const T* Yk = Y + (long long)k * rows * n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -442,8 +446,10 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(const T* __restrict__
 }
 
 template <typename T>
-__global__ void loss_final_kernel(const double* __restrict__ partial, int nblk, int K, double inv_norm, T* losses) {
+__global__ void loss_final_kernel(const double* __restrict__ partial, int nblk, int K, double inv_norm, T* losses,
+                                  const int* __restrict__ need = nullptr) {
     const int k = blockIdx.x;
+    if (need && !need[k]) return;
     double acc = 0;
     for (int j = threadIdx.x; j < nblk; j += blockDim.x) acc += partial[(long long)k * nblk + j];
     __shared__ double sh[8];

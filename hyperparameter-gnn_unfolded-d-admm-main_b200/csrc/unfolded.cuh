@@ -117,7 +117,8 @@ template <typename T>
 struct LevelFwdParams {
     int B, P, n, TB, first, list_cap;   // list_cap: shared-memory ints reserved per problem for its neighbour list
     int csplit;                         // CTAs per problem group (each walks nchunks/csplit consecutive chunks)
-    const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // event lists (exact order)
+    const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // event lists (exact order), or plain adjacency lists when !exact_order
+    int exact_order;                    // 1: 2L y accumulated in the reference's event order (bit-identical delta); 0: see lean::lap_half
     const T *hyp_k, *hyp_prev;          // rows [P,4] of the table
     T G, V, D, Uc_prev;
     int hasD;
@@ -886,9 +887,12 @@ __global__ void __launch_bounds__(256) loss_sums_partial_kernel(const T* __restr
         part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = t;
     }
 }
+// need[k] = 1 where sum Y^2 - 2 <S, label> + P sum label^2 cancels more than three digits (a near-converged iterate: the
+// fp32 partial sums behind S and sum Y^2 then no longer carry the loss to fp32 accuracy) -- the caller re-evaluates those
+// iterations from Y
 template <typename T>
 __global__ void __launch_bounds__(256) loss_sums_final_kernel(const double* __restrict__ part, int nblk, const double* __restrict__ sumsq,
-                                                              int P, double inv, T* __restrict__ losses) {
+                                                              int P, double inv, T* __restrict__ losses, int* __restrict__ need) {
     const int k = blockIdx.x;
     double d = 0, l2 = 0;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
@@ -903,7 +907,9 @@ __global__ void __launch_bounds__(256) loss_sums_final_kernel(const double* __re
     if (threadIdx.x == 0) {
         double td = 0, tl = 0;
         for (int w = 0; w < 8; ++w) { td += sh[0][w]; tl += sh[1][w]; }
-        losses[k] = (T)((sumsq[k] - 2.0 * td + (double)P * tl) * inv);
+        const double sse = sumsq[k] - 2.0 * td + (double)P * tl;
+        losses[k] = (T)(sse * inv);
+        if (need) need[k] = (sse < 1e-3 * (sumsq[k] + (double)P * tl)) ? 1 : 0;
     }
 }
 

@@ -120,6 +120,21 @@ __device__ __forceinline__ Q4 lap_events(const unsigned char* tile_lane, const Q
     }
     return Q4{a, b};
 }
+// 2L x = 2 sum_{j in N(q)} (x_q - x_j) over the plain neighbour list: the same differences the event order accumulates
+// (each of them twice, interleaved with the other endpoint's visits), taken once and doubled -- half the shared-memory
+// gathers and additions.  Differences first, so nothing cancels that the reference's form does not cancel; the result is
+// the reference's delta to rounding (a few ulp), not to the bit.  ncu (round 2) has the forward level's L1 data pipe 74-87 %
+// busy, 60 % of it with the event gather: this, not DRAM, is what the level waits for.
+__device__ __forceinline__ Q4 lap_half(const unsigned char* tile_lane, const Q4& xq, const int32_t* sOff, int e0, int e1) {
+    u64 a = 0ull, b = 0ull;
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+        const Q4 xj = ldq(tile_lane + sOff[e]);
+        a = add2(a, sub2(xq.a, xj.a));
+        b = add2(b, sub2(xq.b, xj.b));
+    }
+    return Q4{add2(a, a), add2(b, b)};
+}
 // 2L x = 2 (deg x_q - sum_j x_j) over the plain neighbour list (backward: no bit pattern to reproduce)
 __device__ __forceinline__ Q4 lap_adj(const unsigned char* tile_lane, const Q4& xq, const int32_t* sOff, int e0, int e1) {
     u64 a = 0ull, b = 0ull;
@@ -228,7 +243,8 @@ level_fwd_lean_kernel(const LevelFwdParams<float> p) {
                 const float4 h4 = *reinterpret_cast<const float4*>(sHyp + pp * 4);     // alpha_k, tau_k, rho_k, eta_{k-1}
                 const u64 dg2 = dup2(sDeg[bl * P + pp]);
                 const Q4 yv = ldq(tile_lane + pp * ROWB);
-                const Q4 dv = lap_events(tile_lane, yv, loff, lptr[pp], lptr[pp + 1]);
+                const Q4 dv = p.exact_order ? lap_events(tile_lane, yv, loff, lptr[pp], lptr[pp + 1])
+                                            : lap_half(tile_lane, yv, loff, lptr[pp], lptr[pp + 1]);
                 // U_k = clamp(U_{k-1} + d_k eta_{k-1})
                 const u64 eta2 = dup2(h4.w);
                 Uv.a = clamp2(add2(Uv.a, mul2(dv.a, eta2)), Uc);

@@ -178,7 +178,8 @@ level_fwd_pipe_kernel(const LevelFwdParams<float> p, const __grid_constant__ CUt
                 Q4 Uv = ldq(Su + (size_t)r * ROWB + lane_bytes);
                 const float4 h4 = *reinterpret_cast<const float4*>(sHyp + pp * 4);     // alpha_k, tau_k, rho_k, eta_{k-1}
                 const u64 dg2 = dup2(sDeg[bl * P + pp]);
-                const Q4 dv = lap_events(tile_lane, yv, sOff + bl * p.list_cap, lptr[pp], lptr[pp + 1]);
+                const Q4 dv = p.exact_order ? lap_events(tile_lane, yv, sOff + bl * p.list_cap, lptr[pp], lptr[pp + 1])
+                                            : lap_half(tile_lane, yv, sOff + bl * p.list_cap, lptr[pp], lptr[pp + 1]);
                 // U_k = clamp(U_{k-1} + d_k eta_{k-1})
                 const u64 eta2 = dup2(h4.w);
                 Uv.a = clamp2(add2(Uv.a, mul2(dv.a, eta2)), Uc);

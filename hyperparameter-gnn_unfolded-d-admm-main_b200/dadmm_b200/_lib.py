@@ -71,6 +71,7 @@ def _load():
         "dadmm_device_check": (i32, []),
         "dadmm_launch_count": (i64, []),
         "dadmm_set_pdl": (i32, [i32]),
+        "dadmm_set_consensus_order": (i32, [i32]),
         "dadmm_profile_enable": (i32, [i32]),
         "dadmm_profile_read": (i32, [C.POINTER(dbl), C.POINTER(i64)]),
         "dadmm_contract": (i32, [i32, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
@@ -92,7 +93,7 @@ def _load():
         "dadmm_loss_fwd": (i32, [i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, sz, vp]),
         "dadmm_loss_bwd": (i32, [i32, i32, i32, i32, i32, vp, vp, C.POINTER(dbl), vp, vp]),
         "dadmm_loss_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
-        "dadmm_loss_from_sums": (i32, [i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp]),
+        "dadmm_loss_from_sums": (i32, [i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
         "dadmm_gcn_epilogue_fwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
         "dadmm_gcn_epilogue_bwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, vp, vp, vp, vp]),
         "dadmm_gcn_partial_rows": (i32, [i32, i32]),
@@ -164,6 +165,12 @@ def stream_ptr(dev) -> C.c_void_p:
 def set_pdl(on: bool) -> bool:
     """Programmatic dependent launch of the K-loop chain on/off (``dadmm_set_pdl``); returns the previous setting."""
     return bool(lib.dadmm_set_pdl(int(bool(on))))
+
+
+def set_consensus_order(exact: bool) -> bool:
+    """2 L y of the fused forward levels in the reference's event order (bit-identical delta) or with every neighbour
+    difference taken once and doubled (default; ``dadmm_set_consensus_order``); returns the previous setting."""
+    return bool(lib.dadmm_set_consensus_order(int(bool(exact))))
 
 
 def launch_count() -> int:

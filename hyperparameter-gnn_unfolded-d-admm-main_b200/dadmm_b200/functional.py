@@ -406,6 +406,47 @@ class Unfolded(torch.autograd.Function):
         return (ghyp,) + (None,) * 13
 
 
+def tc_linear_ok(M: int, c_in: int, c_out: int) -> bool:
+    """Do both products of a bias-free linear layer on [M, c_in] rows -- x W^T and g W -- take the tensor-core contraction?"""
+    tc = lib.dadmm_contract_uses_tensor_cores
+    return bool(tc(_lib.F32, _lib.ALGO_AUTO, M, 1, c_out, c_in)) and bool(tc(_lib.F32, _lib.ALGO_AUTO, M, 1, c_in, c_out))
+
+
+class TCLinear(torch.autograd.Function):
+    """y = x W^T for x [M, c_in], W [c_out, c_in] (``nn.Linear`` layout) on the library's fp32-accurate tensor-core
+    contraction (tcgen05, scaled fp16 hi/lo operand pairs: the accuracy of an fp32 FMA loop at several times cuBLAS's fp32
+    SGEMM rate): the dense products of the model-#3 hypernetwork (gnn_dlasso_models_progressive.py:52-68, :93-106), which
+    PyTorch evaluates on the FP32 FMA pipe.  Backward: g W through the same kernel; g^T x (a reduction over the M rows) by
+    cuBLAS."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, W):
+        ctx.save_for_backward(x, W)
+        return contract(W.unsqueeze(0), x.unsqueeze(1)).squeeze(1)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        gx = contract(W.t().contiguous().unsqueeze(0), g.unsqueeze(1)).squeeze(1) if ctx.needs_input_grad[0] else None
+        gW = g.t().mm(x) if ctx.needs_input_grad[1] else None
+        return gx, gW
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear`` with the product on the tensor-core contraction wherever the shape takes it (CUDA, float32, no
+    autocast); otherwise PyTorch's own."""
+    lead, c_in = x.shape[:-1], x.shape[-1]
+    M = int(math.prod(lead)) if lead else 1
+    if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and not torch.is_autocast_enabled()
+            and tc_linear_ok(M, c_in, weight.shape[0])):
+        y = TCLinear.apply(x.reshape(M, c_in).contiguous(), weight).reshape(*lead, weight.shape[0])
+        return y if bias is None else y + bias
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 class GCNEpilogue(torch.autograd.Function):
     """Everything a graph-convolution layer of the model-#3 hypernetwork does after its dense product, for the whole
     batch in one kernel each way (``dadmm_gcn_epilogue_fwd`` / ``_bwd``; reference gnn_dlasso_models_progressive.py:37-72,
@@ -498,7 +539,7 @@ def loss_per_iteration(Y: torch.Tensor, label: torch.Tensor, B_norm: Optional[in
                 while j < K and use[j] == use[k]:
                     j += 1
                 if use[k]:
-                    check(lib.dadmm_loss_from_sums(dt, k, j, B, P, n, Bn, ptr(S), ptr(sq), ptr(lab), ptr(losses), ptr(ws), wsb,
+                    check(lib.dadmm_loss_from_sums(dt, k, j, B, P, n, Bn, ptr(S), ptr(sq), ptr(lab), ptr(Yc), ptr(losses), ptr(ws), wsb,
                                                    stream_ptr(dev)), "dadmm_loss_from_sums")
                 else:
                     exact(k, j)
@@ -553,6 +594,10 @@ class MSELoss(torch.autograd.Function):
             sentinel = torch.zeros((), dtype=Y.dtype, device=Y.device).expand(Y.shape)
             if ctx.handle.offer(label.contiguous(), coefs_dev, sentinel):
                 return sentinel, None, None, None
+        if torch.cuda.is_current_stream_capturing():
+            # under CUDA-graph capture the coefficients cannot visit the host: dense gY = coef[k] (Y[k] - label) in one pass
+            c = (g_losses.detach().to(Y.dtype) * scale).view(K, 1, 1, 1, 1)
+            return (Y - label.view(1, B, 1, Y.shape[3], 1)) * c, None, None, None
         coefs = [float(v) * scale for v in g_losses.detach().to("cpu", torch.float64).tolist()]
         gY = torch.empty_like(Y, memory_format=torch.contiguous_format)
         with device_guard(Y.device):

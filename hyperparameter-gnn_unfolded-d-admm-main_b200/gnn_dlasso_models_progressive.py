@@ -140,7 +140,8 @@ class GNNHypernetwork3(nn.Module):
         if drop and self.dropout.training and self.dropout.p > 0:
             keep = 1.0 - self.dropout.p
             mask = torch.empty((Bn, Pn, conv.lin.out_features), dtype=x.dtype, device=x.device).bernoulli_(keep).div_(keep)
-        out, mean, var = DF.GCNEpilogue.apply(conv.lin(x), adj_hat, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+        H = DF.linear(x, conv.lin.weight) if getattr(self, "tc_linear", True) else conv.lin(x)
+        out, mean, var = DF.GCNEpilogue.apply(H, adj_hat, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                               training_bn, bn.eps, 0.01, mask)
         if training_bn and bn.track_running_stats:
             with torch.no_grad():          # the B sequential running-stat updates of the reference's per-sample calls, in closed form
@@ -228,8 +229,17 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
     def _hyper_packed(self, AtAy, Atb, graph_list, adj_hat=None):
         B = AtAy.shape[0]
         h = torch.cat([AtAy, Atb], dim=2)
-        h = self.fc(self.decoder(self.encoder(h, graph_list, adj_hat)))
+        h = self.fc(self._decode(self.encoder(h, graph_list, adj_hat)))
         return self._scaled(h, B)
+
+    def _decode(self, x):
+        """``self.decoder(x)`` (reference :93-106) with the Linear layers' products on the tensor-core contraction where
+        their shapes take it (``DF.linear``); same modules, same parameters, same order."""
+        if not (getattr(self.encoder, "tc_linear", True) and x.is_cuda and x.dtype == torch.float32):
+            return self.decoder(x)
+        for mod in self.decoder:
+            x = DF.linear(x, mod.weight, mod.bias) if isinstance(mod, nn.Linear) else mod(x)
+        return x
 
     def _scaled(self, h, B):
         """fc output [B, 4*(P|1)] -> [B, 4, P|1, 1, 1] = (alpha, tau, rho, eta): sigmoid, clamp, times the four maxima, tau /

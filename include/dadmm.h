@@ -135,6 +135,12 @@ int64_t dadmm_launch_count(void);
  * (griddepcontrol.wait) before touching anything the predecessor produces.  Results are bit-identical either way;
  * the switch exists for A/B timing and tests.  Returns the previous setting. */
 int dadmm_set_pdl(int on);
+/* Consensus operator delta = 2 L y of the fused forward levels (reference compute_delta, unfolded_DLASSO.py:127-140).
+ * exact = 1: accumulated in the reference's own order of `delta[p] += diff; delta[j] -= diff` events -- bit-identical
+ * delta; exact = 0 (default): every neighbour difference (y_q - y_j) taken once and the sum doubled -- the same value to
+ * a few ulp with half the shared-memory gathers.  The per-iteration entry point dadmm_step_fwd always uses the exact
+ * order.  Returns the previous setting; DADMM_EXACT_ORDER=1 in the environment sets the initial value. */
+int dadmm_set_consensus_order(int exact);
 
 /* Per-kernel-kind timing for bench.py's roofline: after dadmm_profile_enable(1) every launch is bracketed
  * by CUDA events on its stream; dadmm_profile_read sums elapsed ms / launch counts per kind
@@ -244,9 +250,12 @@ int dadmm_loss_fwd(int dtype, int K, int B, int P, int n, int64_t B_norm, const 
 int dadmm_loss_bwd(int dtype, int K, int B, int P, int n, const void* Y, const void* label,
                    const double* coef, void* gY, dadmm_stream_t stream);
 size_t dadmm_loss_ws_bytes(int dtype, int K, int B, int P, int n);
-/* losses[k], k0 <= k < k1, from the side outputs of dadmm_unfolded_fwd (see dadmm_loss_sums); same workspace size. */
+/* losses[k], k0 <= k < k1, from the side outputs of dadmm_unfolded_fwd (see dadmm_loss_sums); same workspace size.
+ * The sums give sum (Y - label)^2 as sum Y^2 - 2 <S, label> + P sum label^2; where that difference cancels more than three
+ * digits (a near-converged iterate) and Y is given, the iteration is re-evaluated exactly from Y[k] on the device (no host
+ * round trip).  Y may be NULL (no re-evaluation). */
 int dadmm_loss_from_sums(int dtype, int k0, int k1, int B, int P, int n, int64_t B_norm, const void* agent_sum,
-                         const double* sumsq, const void* label, void* losses, void* ws, size_t ws_bytes,
+                         const double* sumsq, const void* label, const void* Y, void* losses, void* ws, size_t ws_bytes,
                          dadmm_stream_t stream);
 
 /* Per-problem epilogue of one graph-convolution layer of the model-#3 hypernetwork (fp32 only) -- replaces, for the whole

@@ -292,3 +292,27 @@ def test_losses_from_forward_side_sums_match_the_full_read_of_Y():
     assert math.isclose(float(lm), float(direct.mean()) + 1e-8, rel_tol=2e-6) and math.isclose(float(lf), float(direct[-1]) + 1e-8, rel_tol=1e-7)
     lf.backward()
     assert model.seq_hyp.param.grad is not None and bool(torch.isfinite(model.seq_hyp.param.grad).all())
+
+
+def test_losses_from_sums_near_convergence_fall_back_to_the_exact_evaluation():
+    """A near-converged iterate (Y = label + 1e-3 noise): sum Y^2 - 2 <S, label> + P sum label^2 cancels six digits, so the
+    fp32 partial sums behind it no longer carry the loss; ``dadmm_loss_from_sums`` flags such iterations on the device and
+    re-evaluates them from Y -- the result equals the direct kernel's, while an unconverged iteration keeps the sums."""
+    from dadmm_b200 import functional as DF
+    K, B, P, n = 4, 64, 16, 256
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    label = 2 * torch.randn(B, n, 1, device=DEV, generator=gen)
+    Y = label.view(1, B, 1, n, 1).expand(K, B, P, n, 1).contiguous()
+    Y = Y + 1e-3 * torch.randn(Y.shape, device=DEV, generator=gen)
+    Y[1] = torch.randn(B, P, n, 1, device=DEV, generator=gen)          # one iteration far from the label
+    S = Y[..., 0].sum(dim=2).contiguous()                              # [K,B,n] fp32 agent sums, as the forward level leaves them
+    sq = (Y.float() ** 2).sum(dim=(1, 2, 3, 4)).double()               # fp32-accumulated sum of squares
+    h = DF.FusedLossHandle()
+    h.sums = (S, sq, [True] * K, Y.data_ptr())
+    exact = DF.loss_per_iteration(Y, label)
+    fused = DF.loss_per_iteration(Y, label, None, h)
+    ref = ((Y.double() - label.double().view(1, B, 1, n, 1)) ** 2).mean(dim=(1, 2, 3, 4))
+    assert float(((exact.double() - ref).abs() / ref).max()) < 1e-6
+    assert float(((fused.double() - ref).abs() / ref).max()) < 1e-6, (fused, ref)
+    naive = (sq - 2 * (S.double() * label.double().view(1, B, n)).sum(dim=(1, 2)) + P * (label.double() ** 2).sum()) / (P * B * n)
+    assert float(((naive[0] - ref[0]).abs() / ref[0])) > 1e-5          # the cancellation this guards against is real
