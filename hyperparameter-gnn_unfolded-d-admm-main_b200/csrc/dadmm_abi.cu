@@ -60,7 +60,7 @@ struct StepCfg {
 static bool aligned_to(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // narr_fwd: shared-memory tile arrays the forward needs (0..2); the backward always needs 2 (+R scalars)
-static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, StepCfg* c) {
+static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, StepCfg* c, bool fwd_only = false) {
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t budget = 100 * 1024;  // two CTAs per SM
     int TB = std::max(1, std::min(B, (16 + P - 1) / P));
@@ -73,7 +73,7 @@ static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, S
         for (int tb = TB; tb >= 1; --tb) {
             const size_t R = (size_t)tb * P, CH = 32 * vec;
             const size_t sf = (size_t)narr_fwd * R * CH * es;
-            const size_t sb = 2 * R * CH * es + R * es;
+            const size_t sb = fwd_only ? 0 : 2 * R * CH * es + R * es;
             if (std::max(sf, sb) <= budget || (vec == 1 && tb == 1 && std::max(sf, sb) <= 227 * 1024)) {
                 c->vec = vec;
                 c->TB = tb;
@@ -279,9 +279,14 @@ static int contract_impl(int dtype, int algo, int B, int P, int n_out, int n_in,
 // Tile configuration of a level kernel: `narr` [R][CH] tiles plus (when it fits) the staged neighbour lists of
 // the tile's TB problems.  *list_cap == 0 means "lists stay in global memory".
 static int level_cfg(int dtype, int B, int P, int n, int narr, int max_list, StepCfg* c, size_t* smem, int* list_cap,
-                     int acc_rows = 0) {
+                     int acc_rows = 0, bool fwd_only = false) {
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
-    if (int e = step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), c)) return e;     // same vec/TB/nchunks as step_bwd
+    // backward: same vec/TB/nchunks as step_bwd (the partial-sum layout follows them).  The forward level holds ONE tile and
+    // leaves no partials, so it keeps 128-unknown chunks up to twice the agents (P = 100, BASELINE configs[4]: the two-tile
+    // rule had it on 64-unknown chunks and the generic kernel, 3.7 ms per level instead of ~2)
+    if (int e = fwd_only ? step_cfg(dtype, B, P, n, std::max(narr, 1), max_vec_for(dtype, n), c, true)
+                         : step_cfg(dtype, B, P, n, 2, max_vec_for(dtype, n), c))
+        return e;
     const size_t scal = ((size_t)4 * P + (size_t)c->TB * P) * es;       // staged per-agent scalars (stage_scalars)
     const size_t tiles = (size_t)narr * c->TB * P * 32 * c->vec * es + (size_t)acc_rows * c->TB * P * 4 * es + scal;
     const size_t lists = (size_t)c->TB * ((size_t)P + 1 + (size_t)std::max(max_list, 1)) * 4;
@@ -394,7 +399,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.agent_sum = nullptr; p.sq_part = nullptr;
     StepCfg c;
     size_t smem = 0;
-    if (int e = level_cfg(dtype, B, P, n, p.first ? 0 : 1, g->max_events, &c, &smem, &p.list_cap)) return e;
+    if (int e = level_cfg(dtype, B, P, n, p.first ? 0 : 1, g->max_events, &c, &smem, &p.list_cap, 0, true)) return e;
     if (int e = check_aligned(dtype, c.vec, {y, U_in, d0, a, atb, y_next, U_out, graw})) return e;
     p.TB = c.TB;
     // forward: two 128-unknown chunks per CTA (B200, cfg4, lean kernel: 1 chunk 0.940 ms, 2 -> 0.916, 4 -> 0.919, 8 -> 0.925;

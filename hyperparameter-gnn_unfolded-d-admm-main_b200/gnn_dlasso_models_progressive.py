@@ -140,7 +140,9 @@ class GNNHypernetwork3(nn.Module):
         if drop and self.dropout.training and self.dropout.p > 0:
             keep = 1.0 - self.dropout.p
             mask = torch.empty((Bn, Pn, conv.lin.out_features), dtype=x.dtype, device=x.device).bernoulli_(keep).div_(keep)
-        H = DF.linear(x, conv.lin.weight) if getattr(self, "tc_linear", True) else conv.lin(x)
+        # (DF.linear -- the product on the library's tensor-core contraction -- was measured and lost at these sizes: every
+        # call re-splits both operands into fp16 pairs, 24.6 -> 27.9 ms per graphed step at configs[1]; opt-in via tc_linear)
+        H = DF.linear(x, conv.lin.weight) if getattr(self, "tc_linear", False) else conv.lin(x)
         out, mean, var = DF.GCNEpilogue.apply(H, adj_hat, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                               training_bn, bn.eps, 0.01, mask)
         if training_bn and bn.track_running_stats:
@@ -235,7 +237,7 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
     def _decode(self, x):
         """``self.decoder(x)`` (reference :93-106) with the Linear layers' products on the tensor-core contraction where
         their shapes take it (``DF.linear``); same modules, same parameters, same order."""
-        if not (getattr(self.encoder, "tc_linear", True) and x.is_cuda and x.dtype == torch.float32):
+        if not (getattr(self.encoder, "tc_linear", False) and x.is_cuda and x.dtype == torch.float32):
             return self.decoder(x)
         for mod in self.decoder:
             x = DF.linear(x, mod.weight, mod.bias) if isinstance(mod, nn.Linear) else mod(x)
