@@ -392,7 +392,9 @@ level_bwd_lean_kernel(const LevelBwdParams<float> p) {
                 const float4 h4 = *reinterpret_cast<const float4*>(sHyp + pp * 4);     // alpha_k, tau_k, rho_k, eta_{k-1}
                 const u64 dg2 = dup2(sDeg[bl * P + pp]);
                 const Q4 yv = ldq(tile_lane + pp * ROWB);
-                const Q4 dw = lap_adj(tile_lane, yv, loff, lptr[pp], lptr[pp + 1]);
+                // 2L y_k with the forward level's own rounding (lean::lap_half is its default form): U_k, r_k and every mask
+                // below are then bit for bit the forward's, not a re-evaluation that may fall on the other side of a clamp
+                const Q4 dw = lap_half(tile_lane, yv, loff, lptr[pp], lptr[pp + 1]);
                 const u64 alpha2 = dup2(h4.x), nalpha2 = dup2(-h4.x), tau2 = dup2(h4.y), rho2 = dup2(h4.z), eta2 = dup2(h4.w);
                 Q4 o_ga, o_c, o_dir, o_db;
                 u64 pa2 = 0ull, pt2 = 0ull, pr2 = 0ull, pe2 = 0ull;

@@ -271,9 +271,8 @@ class DLASSO_GNNHyp3_Progressive(nn.Module):
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         adj_hat = graph.normalized_adjacency(W.dtype)                 # cached on the BatchGraph (itself cached per graph_list)
         if noise is None:
-            y0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
-            U0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
-            d0 = torch.randn((B, self.P, self.n, 1), device=device) * 1e-2
+            # torch.randn(...) * 1e-2 three times, in the reference's order (:49-51); scale applied by the generator kernel
+            y0, U0, d0 = DF.initial_noise((B, self.P, self.n, 1), device)
         else:
             y0, U0, d0 = (t.to(device=device, dtype=W.dtype).reshape(B, self.P, self.n, 1) for t in noise)
         deferred = self.check_finite == "deferred"        # sticky flags, read by nonfinite_seen() only (dadmm_b200/graphs.py)

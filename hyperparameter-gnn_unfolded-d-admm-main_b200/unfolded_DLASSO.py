@@ -135,9 +135,8 @@ class DLASSO_unfolded(nn.Module):
         graph = BatchGraph.from_graph_list(graph_list, self.P, device)
         # initial noise: same three draws, same order / shape / device as the reference (:49-51)
         if noise is None:
-            y0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
-            U0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
-            d0 = torch.randn((batch_size, self.P, self.n, 1), device=device) * 1e-2
+            # torch.randn(...) * 1e-2 three times, in the reference's order (:49-51); scale applied by the generator kernel
+            y0, U0, d0 = DF.initial_noise((batch_size, self.P, self.n, 1), device)
         else:
             y0, U0, d0 = (t.to(device=device, dtype=W.dtype).reshape(batch_size, self.P, self.n, 1) for t in noise)
         table = self.seq_hyp.table(K)                                   # [K, P|1, 4]

@@ -317,3 +317,19 @@ def test_losses_from_sums_near_convergence_fall_back_to_the_exact_evaluation():
     assert float(((fused.double() - ref).abs() / ref).max()) < 1e-6, (fused, ref)
     naive = (sq - 2 * (S.double() * label.double().view(1, B, n)).sum(dim=(1, 2)) + P * (label.double() ** 2).sum()) / (P * B * n)
     assert float(((naive[0] - ref[0]).abs() / ref[0])) > 1e-5          # the cancellation this guards against is real
+
+
+def test_initial_noise_is_the_references_three_draws_bit_for_bit():
+    """``DF.initial_noise`` == three ``torch.randn(shape, device) * 1e-2`` in order (unfolded_DLASSO.py:49-51), and the
+    generator is left where the reference leaves it."""
+    from dadmm_b200 import functional as DF
+    shape = (37, 5, 129, 1)
+    torch.manual_seed(11)
+    ref = [torch.randn(shape, device=DEV) * 1e-2 for _ in range(3)]
+    after_ref = torch.randn(5, device=DEV)
+    torch.manual_seed(11)
+    got = DF.initial_noise(shape, DEV)
+    after = torch.randn(5, device=DEV)
+    for a, r in zip(got, ref):
+        assert torch.equal(a, r)
+    assert torch.equal(after, after_ref)
