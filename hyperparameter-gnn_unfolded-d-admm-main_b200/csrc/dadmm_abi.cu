@@ -352,6 +352,13 @@ static int launch_level(K kernel, int grid, int threads, size_t smem, cudaStream
     return 0;
 }
 
+// software prefetch of the warp's next row in the lean level kernels (0 off, 1 into L1, 2 into L2):
+// DADMM_LEVEL_PREFETCH_FWD / _BWD override the defaults
+static int level_prefetch(bool fwd) {
+    static const int f = [] { const char* e = getenv("DADMM_LEVEL_PREFETCH_FWD"); return e ? atoi(e) : -1; }();
+    static const int b = [] { const char* e = getenv("DADMM_LEVEL_PREFETCH_BWD"); return e ? atoi(e) : -1; }();
+    return fwd ? (f >= 0 ? f : 2) : (b >= 0 ? b : 0);
+}
 static int sm_count() {
     static const int n = [] {
         int dev = 0, v = 148;
@@ -389,6 +396,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr);
     p.lst_ptr = g->ev_ptr; p.lst_idx = g->ev_idx; p.deg = g->deg; p.gid = g->graph_id;
     p.exact_order = 1;
+    p.prefetch = level_prefetch(true);
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;
     p.G = (T)cl_k->G; p.V = (T)cl_k->V;
     p.hasD = std::isfinite(cl_k->D) ? 1 : 0;
@@ -519,6 +527,7 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     LevelBwdParams<T> p;
     p.sp = sp;
     p.graw_is_residual = graw_is_residual;
+    p.prefetch = level_prefetch(false);
     p.B = B; p.P = P; p.n = n; p.first = (hyp_prev == nullptr); p.top = top;
     p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx; p.deg = g->deg; p.gid = g->graph_id;
     p.hyp_k = (const T*)hyp_k; p.hyp_prev = (const T*)hyp_prev;

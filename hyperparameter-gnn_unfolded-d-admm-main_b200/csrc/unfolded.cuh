@@ -119,6 +119,7 @@ struct LevelFwdParams {
     int csplit;                         // CTAs per problem group (each walks nchunks/csplit consecutive chunks)
     const int32_t *lst_ptr, *lst_idx, *deg, *gid;   // event lists (exact order), or plain adjacency lists when !exact_order
     int exact_order;                    // 1: 2L y accumulated in the reference's event order (bit-identical delta); 0: see lean::lap_half
+    int prefetch;                       // lean kernels: software prefetch of the warp's next row (0 off, 1 into L1, 2 into L2)
     const T *hyp_k, *hyp_prev;          // rows [P,4] of the table
     T G, V, D, Uc_prev;
     int hasD;
@@ -140,6 +141,7 @@ struct LevelBwdParams {
     int hasD;
     const T *y, *U_prev, *d0, *graw;
     int graw_is_residual;               // 1: `graw` holds AtA y - Atb and r_k is rebuilt here (no saved r_k stream)
+    int prefetch;                       // lean kernel: software prefetch of the warp's next row (0 off, 1 into L1, 2 into L2)
     T *Tb, *C, *ga;
     const T *gY_prev, *label;
     T coef_prev;

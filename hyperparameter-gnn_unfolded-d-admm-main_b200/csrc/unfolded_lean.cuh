@@ -75,6 +75,12 @@ __device__ __forceinline__ float hsum2(u64 v) {
     return a + b;
 }
 
+// software prefetch of a 16-byte-per-lane row access the warp will make one row later (no registers held meanwhile)
+__device__ __forceinline__ void prefetch_row(const float* p, int level) {
+    if (level == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 struct Q4 { u64 a, b; };      // four consecutive fp32 values as two packed pairs (one 16-byte access)
 __device__ __forceinline__ Q4 ldq(const void* p) {
     const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
@@ -240,6 +246,15 @@ level_fwd_lean_kernel(const LevelFwdParams<float> p) {
                 const unsigned off = base + (unsigned)pp * p.n;
                 const Q4 av = ldq_stream(p.a + off);
                 Q4 Uv = ldq_stream(p.U_in + off);
+                if (p.prefetch) {
+                    // next row of this warp; from its last row of the chunk, its first row of the next chunk
+                    const bool more = pp + nwarps < P;
+                    if (more || (p.TB == 1 && chunk + 1 < chunk_end)) {
+                        const unsigned nx = more ? off + (unsigned)nwarps * p.n : base + CH + (unsigned)warp * p.n;
+                        prefetch_row(p.a + nx, p.prefetch);
+                        prefetch_row(p.U_in + nx, p.prefetch);
+                    }
+                }
                 const float4 h4 = *reinterpret_cast<const float4*>(sHyp + pp * 4);     // alpha_k, tau_k, rho_k, eta_{k-1}
                 const u64 dg2 = dup2(sDeg[bl * P + pp]);
                 const Q4 yv = ldq(tile_lane + pp * ROWB);
@@ -389,6 +404,19 @@ level_bwd_lean_kernel(const LevelBwdParams<float> p) {
                 const Q4 uv = ldq_stream(p.U_prev + off);
                 Q4 cv{0ull, 0ull};
                 if (!top) cv = ldq(p.C + off);
+                if (p.prefetch) {
+                    // the ncu source view of this kernel has 18 % of all stall samples on the first use of this row's
+                    // streams (long scoreboard): the gather in between is shorter than an HBM round trip.  Next row of this
+                    // warp; from its last row of the chunk, its first row of the next chunk
+                    const bool more = pp + nwarps < P;
+                    if (more || (p.TB == 1 && chunk + 1 < chunk_end)) {
+                        const unsigned nx = more ? off + (unsigned)nwarps * p.n : base + CH + (unsigned)warp * p.n;
+                        prefetch_row(p.Tb + nx, p.prefetch);
+                        prefetch_row(p.graw + nx, p.prefetch);
+                        prefetch_row(p.U_prev + nx, p.prefetch);
+                        if (!top) prefetch_row(p.C + nx, p.prefetch);
+                    }
+                }
                 const float4 h4 = *reinterpret_cast<const float4*>(sHyp + pp * 4);     // alpha_k, tau_k, rho_k, eta_{k-1}
                 const u64 dg2 = dup2(sDeg[bl * P + pp]);
                 const Q4 yv = ldq(tile_lane + pp * ROWB);

@@ -72,6 +72,15 @@ def _oracle(A, b, label, graphs, param, noise, dtype, exact):
     return Y.detach(), float(lf.detach()), grad
 
 
+def _oracle_forward(A, b, label, graphs, param, noise, dtype, exact):
+    """Forward-only oracle run (no autograd graph: the configs[4] dimensions would not fit one)."""
+    A, b = A.to(dtype), b.to(dtype)
+    y0, U0, d0 = (t.to(dtype) * 1e-2 for t in noise)
+    table = O.hyp_table(param.to(dtype), MAXP.to(dtype), training=True)
+    hyp = table.expand(table.shape[0], A.shape[1], 4)
+    return O.unfolded_forward(O.atx(A, A), O.atx(A, b), graphs, y0, U0, d0, hyp, exact_delta=exact, gemm_contract=not exact)
+
+
 def _ours(args, A, b, label, graphs, param, noise, algo="auto", two_stage=True):
     import unfolded_DLASSO
     import gnn_dlasso_utils
@@ -159,3 +168,27 @@ def test_configs3_dimensions_full_K_in_a_contracting_regime():
     for k in range(25):
         assert plain[k] <= max(1e-5, 2 * ref[k]), (k, plain[k], ref[k])
         assert trim[k] <= max(1e-5, 2 * ref_trim[k]), (k, trim[k], ref_trim[k])
+
+
+def test_configs4_dimensions_inference_vs_oracle():
+    """BASELINE configs[4] dimensions (P=100, n=2048, m=512, ER p=0.1 bridged; 128 problems, K=3) on the inference path
+    (``no_grad``: no saved streams, U ping-pong, the forward level's one-tile geometry at P=100, two-stage contraction with
+    m=512) against the oracle's fp64 run, with the oracle's bit-faithful fp32 run as the yardstick."""
+    import unfolded_DLASSO
+    import gnn_dlasso_utils
+    w, args, A, b, label, graphs, param, noise = _problem("cfg5", B=128, K=3)
+    with torch.no_grad():
+        Y64 = _oracle_forward(A, b, label, graphs, param, noise, torch.float64, exact=False)
+        Y32 = _oracle_forward(A, b, label, graphs, param, noise, torch.float32, exact=True)
+        model = unfolded_DLASSO.DLASSO_unfolded(A.to(DEV), args).to(DEV)
+        model.seq_hyp.param.copy_(param)
+        Y, _ = model(b.to(DEV), graphs, noise=[t.to(DEV) * 1e-2 for t in noise])
+        lm, lf = gnn_dlasso_utils.compute_loss(Y, label.to(DEV))
+    Y = Y.cpu()
+    l64 = float(O.loss(Y64, label.double(), vectorised=True)[1])
+    plain = [rel_l2(Y[k], Y64[k]) for k in range(w["K"])]
+    ref = [rel_l2(Y32[k], Y64[k]) for k in range(w["K"])]
+    print(f"\nconfigs[4] dims, inference: Y[k] vs oracle fp64 rel-L2 {plain}; oracle fp32 vs fp64 {ref}; loss {float(lf):.7f} vs {l64:.7f}")
+    for k in range(w["K"]):
+        assert plain[k] <= max(1e-5, 2 * ref[k]), (k, plain[k], ref[k])
+    assert abs(float(lf) - l64) <= 1e-5 * abs(l64)
