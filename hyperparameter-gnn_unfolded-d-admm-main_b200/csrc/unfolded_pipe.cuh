@@ -1,5 +1,11 @@
 // unfolded_pipe.cuh -- forward level kernel of the fused fp32 path as a persistent, warp-specialised TMA pipeline.
 //
+// STATUS: an experiment that LOST, kept selectable (DADMM_FWD_PIPE=1; parity-green under the full GPU suite) because the
+// measurement is the point: 1.34 ms per level with one bulk copy per tile row, 1.16 ms with one tiled tensor-map copy per
+// tensor, against 0.84 ms for the occupancy-driven kernel of unfolded_lean.cuh (B200, config 4; DESIGN.md section 4,
+// finding 3).  Two 77 KB stages per SM put the reads on HBM in bursts, 17 warps hide less gather latency than 40, and
+// shared memory has no room for a third stage at P = 50.  The default path does not launch this kernel.
+//
 // Why (ncu, round 2, profiles/r02_ncu_levels_gen2.txt): the occupancy-driven level kernels (unfolded.cuh, unfolded_lean.cuh)
 // run the forward level at 5.3 TB/s alone and 4.9 TB/s inside the power-capped step; their warps spend 7 of every 12
 // stalled cycles on the long scoreboard (the row's `a` and `U` loads, issued by the same warp that needs them a few

@@ -472,6 +472,36 @@ class TCLinear(torch.autograd.Function):
         return gx, gW
 
 
+class SplitKLinear(torch.autograd.Function):
+    """y = x W^T for tall x [M, c_in] (M = B*P rows of the hypernetwork's GCN layers), products by cuBLAS.  The weight
+    gradient g^T x reduces over the M rows; as ONE GEMM its output has (c_out/64)(c_in/64) ~ 49 tiles for 148 SMs and a
+    5120-long k loop (52 us per call at configs[1], a third of the step's GEMM time: torch-profiler view in
+    profiles/r02_model3_torch_profiler.txt).  Here the reduction is cut into SPLIT batched products summed afterwards."""
+    SPLIT = 8
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, W):
+        ctx.save_for_backward(x, W)
+        return x.matmul(W.t())
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        lead = x.shape[:-1]
+        x2, g2 = x.reshape(-1, x.shape[-1]), g.reshape(-1, g.shape[-1])
+        gx = g2.matmul(W).reshape(*lead, W.shape[1]) if ctx.needs_input_grad[0] else None
+        gW = None
+        if ctx.needs_input_grad[1]:
+            M, S = x2.shape[0], SplitKLinear.SPLIT
+            if M >= 2048 and M % S == 0:
+                gW = torch.bmm(g2.reshape(S, M // S, -1).transpose(1, 2), x2.reshape(S, M // S, -1)).sum(dim=0)
+            else:
+                gW = g2.t().matmul(x2)
+        return gx, gW
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.linear`` with the product on the tensor-core contraction wherever the shape takes it (CUDA, float32, no
     autocast); otherwise PyTorch's own."""

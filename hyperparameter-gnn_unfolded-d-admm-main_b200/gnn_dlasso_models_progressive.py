@@ -142,7 +142,12 @@ class GNNHypernetwork3(nn.Module):
             mask = torch.empty((Bn, Pn, conv.lin.out_features), dtype=x.dtype, device=x.device).bernoulli_(keep).div_(keep)
         # (DF.linear -- the product on the library's tensor-core contraction -- was measured and lost at these sizes: every
         # call re-splits both operands into fp16 pairs, 24.6 -> 27.9 ms per graphed step at configs[1]; opt-in via tc_linear)
-        H = DF.linear(x, conv.lin.weight) if getattr(self, "tc_linear", False) else conv.lin(x)
+        if getattr(self, "tc_linear", False):
+            H = DF.linear(x, conv.lin.weight)
+        elif getattr(self, "split_k", True) and x.requires_grad | conv.lin.weight.requires_grad:
+            H = DF.SplitKLinear.apply(x, conv.lin.weight)          # same products; the weight gradient as a split reduction
+        else:
+            H = conv.lin(x)
         out, mean, var = DF.GCNEpilogue.apply(H, adj_hat, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                               training_bn, bn.eps, 0.01, mask)
         if training_bn and bn.track_running_stats:

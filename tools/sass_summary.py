@@ -17,7 +17,7 @@ MNEMONICS = [("UTC*MMA", r"\bUTC[A-Z]*MMA\b", "tcgen05.mma"), ("LDTM", r"\bLDTM\
              ("LDGSTS", r"\bLDGSTS\b", "cp.async"), ("SYNCS", r"\bSYNCS\b", "mbarrier"),
              ("ACQBULK", r"\bACQBULK\b", "griddepcontrol.wait"), ("PREEXIT", r"\bPREEXIT\b", "griddepcontrol.launch_dependents"),
              ("HMMA", r"\bHMMA\b", "legacy mma.sync (none expected)"), ("STL/LDL", r"\b(STL|LDL)\b", "local-memory spills"),
-             ("SHFL", r"\bSHFL\b", "warp shuffles"), ("FFMA", r"\bFFMA\b", "fp32 FMA"), ("DFMA", r"\bDFMA\b", "fp64 FMA")]
+             ("F*2", r"\b(FADD2|FMUL2|FFMA2)\b", "packed fp32x2 arithmetic"), ("SHFL", r"\bSHFL\b", "warp shuffles"), ("FFMA", r"\bFFMA\b", "fp32 FMA"), ("DFMA", r"\bDFMA\b", "fp64 FMA")]
 
 
 def demangle(names):
