@@ -176,6 +176,7 @@ struct Params {
     int* t_exp;                    // device: exponent of the t split (written by one thread)
     const unsigned* w_l1;          // device: max row L1 norm of the operator, float bits
     const unsigned* sub_amax;      // device, with t_hi && sub: max |sub| bits (joins the bound of t = F1 x - sub)
+    int seed_prefetch;             // 1: L2 prefetch of the next tile's seed values (`+=` / `- sub` epilogues)
 };
 
 template <int NT>
@@ -352,6 +353,23 @@ contract_f16_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_con
                     const float* sp = srow + (long long)b0 * p.o_sb;
 #pragma unroll
                     for (int c = 0; c < COLS_PER_THREAD; ++c, sp += p.o_sb) acc[c] = __ldcs(sp);
+                    // The seeds are needed at the first partial sum of the tile, one HBM round trip after these loads issue:
+                    // a seeded second stage took 0.42 ms against 0.28 ms unseeded (round 2, ncu: tensor pipe 43 % against
+                    // 69 %).  The accumulators hold the whole register budget, so the NEXT tile's seeds are pulled into L2
+                    // with prefetches instead (no registers; a tile, ~10 us, ahead; `+=` epilogues only, see launch()).
+                    if (p.seed_prefetch) {
+                        const int tn = t + num_clusters;
+                        if (tn < p.total_tiles) {
+                            const int agn = tn / tiles_per_agent, rn = tn % tiles_per_agent;
+                            const int i0n = (rn % p.m_tiles) * 256 + (int)rank * 128, b0n = (rn / p.m_tiles) * NT + h * COLS_PER_THREAD;
+                            if (i0n + 128 <= p.n_out && b0n + COLS_PER_THREAD <= p.B) {
+                                const float* pn = (p.accumulate ? p.out : p.sub) + (long long)agn * p.n_out + (i0n + q * 32 + lane) +
+                                                  (long long)b0n * p.o_sb;
+#pragma unroll 8
+                                for (int c = 0; c < COLS_PER_THREAD; ++c, pn += p.o_sb) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+                            }
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < COLS_PER_THREAD; ++c) {
@@ -590,6 +608,12 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
     p.exp_w = w.exp; p.exp_x = x.exp; p.amax_out = amax_out; p.sub = sub; p.fast = fast;
     p.kbc = kb_per_chunk(n_in, kbc);
     p.t_hi = p.t_lo = nullptr; p.t_ld = 0; p.t_exp = nullptr; p.w_l1 = w.l1; p.sub_amax = sub_amax;
+    {
+        // measured (B200, cfg4, interleaved A/B): `+=` second stage 19.2 -> 18.4 ms per step; the `- sub` first stage gets
+        // slower with it (15.6 -> 16.0 ms: its seeds are a quarter the size and the tensor pipe, not the seeds, paces it)
+        static const int pf = [] { const char* e = getenv("DADMM_SEED_PREFETCH"); return e ? atoi(e) : 1; }();
+        p.seed_prefetch = (pf == 2) ? 1 : (pf == 1 ? (accumulate ? 1 : 0) : 0);
+    }
     if (tprep && sub && !sub_amax) DADMM_FAIL(-1, "contract_f16: a first stage with a subtracted term needs its max |.|");
     if (tprep) {
         const Split t = split_view(tprep, (long long)B * P, n_out);
