@@ -528,6 +528,9 @@ inline int kb_per_chunk(int n_in, int wanted = 0) {
     }();
     if (forced) return forced;
     if (wanted > 0) return wanted;
+    // (round 2 tried 128-k partial sums below n = 1024 as well -- configs[2], n = 256: 11.1 -> 10.5 ms per step -- and took it
+    // back: at 3.7e-7 per contraction against the FMA loop's 2.0e-7 at K = 256 the tensor-core trajectory is no longer
+    // "no worse than the FMA path" in the expanding regime, which test_unfolded_tc_vs_simt_vs_fp64_oracle asserts)
     return n_in >= 1024 ? KB_PER_CHUNK : 1;
 }
 
