@@ -561,7 +561,12 @@ static int level_bwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
             // lean form: the fused fp16 training path on full tiles, levels k >= 1 (see level_bwd_kernel)
             const bool lean = !p.first && graw_is_residual && !p.hasD && !gY_prev && (n % 128) == 0 && (B % c.TB) == 0;
             static const bool bwd_gen1 = [] { const char* e = getenv("DADMM_BWD_GEN"); return e && atoi(e) == 1; }();
-            if (lean && p.list_cap > 0 && lean_gen2() && !bwd_gen1) {
+            // level k = 0 of the fused training path: a streaming reduction (no gather, nothing propagated)
+            const bool lean_first = p.first && graw_is_residual && !p.hasD && !gY_prev && (n % 128) == 0 && (B % c.TB) == 0 && lean_gen2() && !bwd_gen1;
+            if (lean_first) {
+                if (int e = launch_level(lean::level_bwd_first_lean_kernel<kStepThreads>, c.grid, kStepThreads, smem, s, p)) return e;
+            }
+            else if (lean && p.list_cap > 0 && lean_gen2() && !bwd_gen1) {
                 const int mb = lean_minb(false);
                 if (level_ten_warps(c.TB * P)) {
                     if (int e = mb <= 2 ? launch_level(lean::level_bwd_lean_kernel<320, 2>, c.grid, 320, smem, s, p)

@@ -638,12 +638,20 @@ class MSELoss(torch.autograd.Function):
     When Y comes straight from ``Unfolded`` (``Y._dadmm_handle`` set by the module), backward hands the
     gradient to the reverse sweep as (label, coef[k]) -- the kernel synthesises
     gY[k] = coef[k]*(Y[k]-label) on the fly -- and returns a stride-0 zero placeholder instead of a
-    dense [K,B,P,n] tensor.  Otherwise it materialises gY with ``dadmm_loss_bwd``."""
+    dense [K,B,P,n] tensor.  Otherwise it materialises gY with ``dadmm_loss_bwd``.
+
+    Restriction of the fused route: the gradient with respect to Y itself is not materialised, so anything that observes
+    it -- ``Y.retain_grad()``, a hook on Y, ``torch.autograd.grad(loss, Y)`` -- would see zeros.  ``Y.retain_grad()`` and
+    hooks registered before ``compute_loss`` are detected and take the dense route; for ``autograd.grad(loss, Y)`` delete
+    ``Y._dadmm_handle`` first.  An offer the reverse sweep never collected (a backward pass that stopped at Y) is dropped
+    by the next forward pass or loss evaluation, never applied to a later one."""
 
     @staticmethod
     def forward(ctx, Y, label, B_norm, handle):
         same_dtype("MSELoss", Y, label=label)
         ctx.save_for_backward(Y, label)
+        if handle is not None and (Y.retains_grad or Y._backward_hooks):
+            handle = None                 # someone wants to see d loss / d Y: dense route
         ctx.B_norm, ctx.handle = B_norm, handle
         if handle is not None:
             handle.pending = None         # a (label, coef) offer is valid for the backward pass of THIS loss only
