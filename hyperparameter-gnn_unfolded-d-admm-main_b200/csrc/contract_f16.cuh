@@ -561,16 +561,27 @@ inline int encode3(tc::EncodeTiledFn enc, CUtensorMap* m, const void* ptr, cuuin
 // xprep = split of x viewed as [B*P][n_in]
 // tprep != nullptr: first stage of a two-stage contraction -- the result leaves as the split buffer `tprep`
 // ([B*P][n_out], wprep must have been split with want_l1) and `out` is not written
-// batch-tile width: 256 columns per CTA pair unless that leaves fewer than three waves of tiles (DADMM_F16_NT=128|256 forces one)
-inline int batch_tile(int B, int P, int n_out, int clusters) {
+// batch-tile width: 256 columns per CTA pair unless that leaves too few waves of tiles (DADMM_F16_NT=128|256 forces one,
+// DADMM_F16_NT_WAVES the threshold).  Round 1 drew the line at three waves.  Round 2 measured, at 5.4 waves of 256-wide tiles
+// (interleaved A/B, profiles/r02_tile_width.txt): the second stage (contraction length m = 256, the tile is mostly seeded
+// epilogue) is 9 % FASTER on 128-wide tiles (2.90 -> 2.65 ms at 512 problems), the first stage (contraction length n = 1024,
+// the tile is mostly main loop and the wider tile halves the operator re-reads) 5 % SLOWER (8.66 -> 9.17 ms at 2048 problems).
+// So short contractions switch at six waves, long ones at three.
+inline int batch_tile(int B, int P, int n_in, int n_out, int clusters) {
     static const int forced = [] {
         const char* e = getenv("DADMM_F16_NT");
         const int x = e ? atoi(e) : 0;
         return (x == 128 || x == 256) ? x : 0;
     }();
     if (forced) return forced;
+    static const int waves = [] {
+        const char* e = getenv("DADMM_F16_NT_WAVES");
+        const int x = e ? atoi(e) : 0;
+        return x > 0 ? x : 0;
+    }();
+    const int w = waves ? waves : (n_in <= 256 ? 6 : 3);
     const long long tiles256 = (long long)P * ceil_div(n_out, 256) * ceil_div(B, 256);
-    return tiles256 < 3LL * clusters ? 128 : 256;
+    return tiles256 < (long long)w * clusters ? 128 : 256;
 }
 
 template <int NT>
@@ -628,7 +639,7 @@ inline int launch(int B, int P, int n_out, int n_in, void* wprep, void* xprep, f
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    if (batch_tile(B, P, n_out, num_sms / 2) == 128)
+    if (batch_tile(B, P, n_in, n_out, num_sms / 2) == 128)
         return launch_nt<128>(p, x, n_in, B, P, enc, mwh, mwl, num_sms, tprep != nullptr, s);
     return launch_nt<256>(p, x, n_in, B, P, enc, mwh, mwl, num_sms, tprep != nullptr, s);
 }
