@@ -28,3 +28,16 @@ cuda_total = sum(getattr(e, "self_device_time_total", getattr(e, "self_cuda_time
 print(f"sum of GPU kernel time: {cuda_total:.1f} ms; ops recorded: {sum(e.count for e in ka)}")
 print(ka.table(sort_by="self_cuda_time_total", row_limit=18, max_name_column_width=60))
 print(ka.table(sort_by="self_cpu_time_total", row_limit=12, max_name_column_width=60))
+# kernels only, grouped by name (the op rows above double-count: an op's row includes its kernels)
+from collections import defaultdict
+from torch.autograd import DeviceType
+acc = defaultdict(lambda: [0.0, 0])
+for e in prof.events():
+    if e.device_type == DeviceType.CUDA:
+        dur = getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0) or (e.time_range.end - e.time_range.start)
+        acc[e.name][0] += dur / 1e3
+        acc[e.name][1] += 1
+tot = sum(v[0] for v in acc.values())
+print(f"GPU kernels only: {tot:.2f} ms in {sum(v[1] for v in acc.values())} launches")
+for name, (ms, cnt) in sorted(acc.items(), key=lambda kv: -kv[1][0])[:45]:
+    print(f"{ms:8.3f} ms {cnt:5d} x {ms / cnt * 1e3:7.1f} us  {name[:150]}")
