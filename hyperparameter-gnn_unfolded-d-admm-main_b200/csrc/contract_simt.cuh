@@ -206,8 +206,94 @@ int launch_contract_simt_cfg(const GemmParams<T>& p, cudaStream_t s) {
     return 0;
 }
 
+// ---- skinny batches (B <= 64: the reference's own runs use 16..64 problems per step) -------------------------------------
+// At B = 32, P = 5, n = 500 the tiled kernel above has 40 CTAs walking a 32-step k loop with a barrier per step: 36 us per
+// launch, 56 % of the GPU time of a configs[0] training step (ncu launch list, round 2).  The work is 80 MFLOP against a
+// 5 MB operator that lives in L2 -- a few microseconds if every SM takes part.  Here a CTA owns 16 output rows x 32
+// problems of one agent and its 8 warps SPLIT the contraction index between them (warp w takes the 16-byte groups
+// w, w + 8, ...; the 8 warps together read 128 contiguous bytes of each row per step); a lane holds a 4 x 4 block of the
+// outputs and feeds it from 16-byte loads straight from global memory / L1 (no shared-memory staging, no barrier in the
+// loop); the eight partial sums are added in warp order through shared memory at the end: deterministic, and a fixed
+// summation tree instead of the k-ascending chain of the tiled kernel (the reference's torch.matmul promises neither).
+constexpr int kSkinnyRows = 16, kSkinnyBatch = 32, kSkinnyWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kSkinnyWarps * 32) contract_skinny_kernel(const GemmParams<T> p) {
+    __shared__ __align__(16) T red[kSkinnyWarps][kSkinnyRows * kSkinnyBatch];
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = lane & 3, bg = lane >> 2;                       // 4 row groups x 8 batch groups of 4
+    const int i0 = blockIdx.x * kSkinnyRows, b0 = blockIdx.y * kSkinnyBatch, ag = blockIdx.z;
+    const T* wrow[4];
+    const T* xrow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                                   // out-of-range rows / problems read the last valid one
+        const int i = min(i0 + rg * 4 + j, p.M - 1), b = min(b0 + bg * 4 + j, p.B - 1);
+        wrow[j] = p.W + (long long)ag * p.w_sp + (long long)i * p.w_si;
+        xrow[j] = p.X + (long long)ag * p.x_sp + (long long)b * p.x_sb;
+    }
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = (T)0;
+    const int nk4 = p.Kd >> 2;
+#pragma unroll 2
+    for (int k4 = warp; k4 < nk4; k4 += kSkinnyWarps) {
+        Vec<T, 4> w[4], x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = ld_vec<T, 4>(wrow[j] + 4 * k4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ld_vec<T, 4>(xrow[j] + 4 * k4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(w[a].v[kk], x[c].v[kk], acc[a][c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                                   // red[warp][b][i]: 4 consecutive rows per store
+        Vec<T, 4> v;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v.v[a] = acc[a][c];
+        st_vec<T, 4>(&red[warp][(bg * 4 + c) * kSkinnyRows + rg * 4], v);
+    }
+    __syncthreads();
+    T* Op = p.O + (long long)ag * p.o_sp;
+    for (int o = threadIdx.x; o < kSkinnyRows * kSkinnyBatch; o += kSkinnyWarps * 32) {
+        const int i = i0 + o % kSkinnyRows, b = b0 + o / kSkinnyRows;
+        if (i >= p.M || b >= p.B) continue;
+        T sum = red[0][o];
+#pragma unroll
+        for (int w = 1; w < kSkinnyWarps; ++w) sum += red[w][o];
+        T* q = Op + (long long)b * p.o_sb + (long long)i * p.o_si;
+        *q = p.accumulate ? (*q + sum) : sum;
+    }
+}
+
+template <typename T>
+int launch_contract_skinny(const GemmParams<T>& p, cudaStream_t s) {
+    dim3 grid(ceil_div(p.M, kSkinnyRows), ceil_div(p.B, kSkinnyBatch), p.P);
+    ProfScope prof(PROF_CONTRACT_SIMT, s);
+    DADMM_CUDA(launch_chain(contract_skinny_kernel<T>, grid, dim3(kSkinnyWarps * 32), 0, s, p));
+    DADMM_LAUNCHED();
+    return 0;
+}
+
+inline bool skinny_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("DADMM_SKINNY");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 template <typename T, int WMODE, int XMODE>
 int launch_contract_simt_modes(const GemmParams<T>& p, cudaStream_t s) {
+    if constexpr (WMODE == LD_VEC_K && XMODE == LD_VEC_K)
+        if (p.B <= 64 && skinny_enabled()) return launch_contract_skinny<T>(p, s);
     if (p.B <= 64) return launch_contract_simt_cfg<T, SimtCfgSmall<T>, WMODE, XMODE>(p, s);
     return launch_contract_simt_cfg<T, SimtCfg<T>, WMODE, XMODE>(p, s);
 }

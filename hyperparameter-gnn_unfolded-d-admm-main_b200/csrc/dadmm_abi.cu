@@ -59,15 +59,17 @@ struct StepCfg {
 
 static bool aligned_to(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+static int forced_tb() {
+    static const int forced = [] { const char* e = getenv("DADMM_STEP_TB"); return e ? atoi(e) : 0; }();   // experiment knob
+    return forced;
+}
+
 // narr_fwd: shared-memory tile arrays the forward needs (0..2); the backward always needs 2 (+R scalars)
 static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, StepCfg* c, bool fwd_only = false) {
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t budget = 100 * 1024;  // two CTAs per SM
     int TB = std::max(1, std::min(B, (16 + P - 1) / P));
-    {
-        static const int forced = [] { const char* e = getenv("DADMM_STEP_TB"); return e ? atoi(e) : 0; }();   // experiment knob
-        if (forced > 0) TB = std::max(1, std::min(B, forced));
-    }
+    if (forced_tb() > 0) TB = std::max(1, std::min(B, forced_tb()));
     for (int vec = max_vec; vec >= 1; vec >>= 1) {
         if (n % vec) continue;
         for (int tb = TB; tb >= 1; --tb) {
@@ -75,9 +77,12 @@ static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, S
             const size_t sf = (size_t)narr_fwd * R * CH * es;
             const size_t sb = fwd_only ? 0 : 2 * R * CH * es + R * es;
             if (std::max(sf, sb) <= budget || (vec == 1 && tb == 1 && std::max(sf, sb) <= 227 * 1024)) {
+                c->nchunks = (n + (int)CH - 1) / (int)CH;
+                // skinny batches (the reference's own B = 16..64): fewer problems per tile until there is a CTA per SM
+                // (configs[0], B = 32, P = 5: TB = 4 left 16 / 32 CTAs, 20 / 17 us per forward / backward level)
+                while (tb > 1 && !forced_tb() && (long long)((B + tb - 1) / tb) * c->nchunks < 148) --tb;
                 c->vec = vec;
                 c->TB = tb;
-                c->nchunks = (n + (int)CH - 1) / (int)CH;
                 c->grid = c->nchunks * ((B + tb - 1) / tb);
                 c->smem_fwd = sf;
                 c->smem_bwd = sb;
@@ -415,7 +420,9 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
     // DADMM_FWD_CHUNKS_PER_CTA overrides.
     {
         static const int forced = [] { const char* e = getenv("DADMM_FWD_CHUNKS_PER_CTA"); return e ? atoi(e) : 0; }();
-        const int cpc = forced > 0 ? forced : 2;
+        const int groups = (B + c.TB - 1) / c.TB;
+        // (one chunk per CTA while two would leave SMs without a CTA)
+        const int cpc = forced > 0 ? forced : ((long long)groups * ((c.nchunks + 1) / 2) < 148 ? 1 : 2);
         p.csplit = std::max(1, (c.nchunks + cpc - 1) / cpc);
     }
     c.grid = ((B + c.TB - 1) / c.TB) * p.csplit;
