@@ -920,6 +920,14 @@ int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in, const
                          accumulate, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int dadmm_contract_prepared(int dtype, int algo, int B, int P, int n_out, int n_in, const void* W, int64_t w_sp, int64_t w_si,
+                            int64_t w_sk, const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk, void* out, int64_t o_sb,
+                            int64_t o_sp, int64_t o_si, int accumulate, void* ws, size_t ws_bytes, int w_prepared,
+                            dadmm_stream_t stream) {
+    return contract_impl(dtype, algo, B, P, n_out, n_in, W, w_sp, w_si, w_sk, x, x_sb, x_sp, x_sk, out, o_sb, o_sp, o_si,
+                         accumulate, ws, ws_bytes, (cudaStream_t)stream, w_prepared != 0);
+}
+
 size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in) {
     return contract_ws_bytes(dtype, algo, B, P, n_out, n_in);
 }

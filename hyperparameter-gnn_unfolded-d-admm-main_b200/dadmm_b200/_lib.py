@@ -14,7 +14,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("DADMM_LIB", os.path.join(_PKG_DIR, "libdadmm_sm100.so"))
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_3XF16, ALGO_TC_F16X1 = 0, 1, 2, 3, 4
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC_3XTF32, "tc_3xtf32": ALGO_TC_3XTF32, "tf32": ALGO_TC_3XTF32,
@@ -76,6 +76,8 @@ def _load():
         "dadmm_profile_read": (i32, [C.POINTER(dbl), C.POINTER(i64)]),
         "dadmm_contract": (i32, [i32, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
                                  i32, vp, sz, vp]),
+        "dadmm_contract_prepared": (i32, [i32, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
+                                          i32, vp, sz, i32, vp]),
         "dadmm_contract_ws_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
         "dadmm_contract_uses_tensor_cores": (i32, [i32, i32, i32, i32, i32, i32]),
         "dadmm_step_fwd": (i32, [i32, i32, i32, i32, GP, CP, HP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -107,9 +107,38 @@ def _state3(t: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # raw ops
 # ---------------------------------------------------------------------------------------------
+class _ContractWsCache:
+    """Workspaces of ``contract(..., constant_operator=True)`` kept between calls: the tensor-core routes leave the
+    operator's scaled fp16 hi/lo copy at the front of the workspace, and while the operator (storage, version, shape), the
+    batch size and the stream stay the same the next call skips the operator's two split passes
+    (``dadmm_contract_prepared``).  Model #3 multiplies by the same AtA once per iteration, forward and backward
+    (gnn_dlasso_models_progressive.py:158-162, :199-203): 30 of its 60 operand splits per step at configs[1]."""
+    MAX = 8
+
+    def __init__(self):
+        self.entries = OrderedDict()
+
+    def lookup(self, W, B, wsb, dev):
+        key = (W.data_ptr(), W._version, tuple(W.shape), B, wsb, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        ent = self.entries.get(key)
+        if ent is None:
+            ent = [torch.empty(wsb, dtype=torch.uint8, device=dev), False, W]     # W: its storage cannot be recycled while cached
+            self.entries[key] = ent
+            while len(self.entries) > self.MAX:
+                self.entries.popitem(last=False)
+        else:
+            self.entries.move_to_end(key)
+        return ent
+
+
+_contract_ws = _ContractWsCache()
+
+
 def contract(W: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
-             algo="auto") -> torch.Tensor:
-    """out[b,p,:] (+)= W[p] @ x[b,p,:].  W [P,n_out,n_in], x [B,P,n_in] -> out [B,P,n_out]."""
+             algo="auto", constant_operator: bool = False) -> torch.Tensor:
+    """out[b,p,:] (+)= W[p] @ x[b,p,:].  W [P,n_out,n_in], x [B,P,n_in] -> out [B,P,n_out].
+    ``constant_operator``: W is a constant of the caller (in-place updates through PyTorch are noticed by its version
+    counter) -- its operand copy for the tensor-core routes is kept between calls (``_ContractWsCache``)."""
     dev = require_cuda(W, x, out)
     W, x = W.contiguous(), x.contiguous()
     P, n_out, n_in = W.shape
@@ -122,6 +151,13 @@ def contract(W: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = Non
     dt, al = dtype_code(x), _algo(algo)
     with device_guard(dev):
         wsb = lib.dadmm_contract_ws_bytes(dt, al, B, P, n_out, n_in)
+        if constant_operator and wsb and _op_splits.enabled:
+            ent = _contract_ws.lookup(W, B, wsb, dev)
+            check(lib.dadmm_contract_prepared(dt, al, B, P, n_out, n_in, ptr(W), n_out * n_in, n_in, 1, ptr(x), P * n_in, n_in, 1,
+                                              ptr(out), P * n_out, n_out, 1, int(accumulate), ptr(ent[0]), wsb, int(ent[1]),
+                                              stream_ptr(dev)), "dadmm_contract_prepared")
+            ent[1] = True
+            return out
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
         check(lib.dadmm_contract(dt, al, B, P, n_out, n_in, ptr(W), n_out * n_in, n_in, 1, ptr(x), P * n_in, n_in, 1,
                                  ptr(out), P * n_out, n_out, 1, int(accumulate), ptr(ws), wsb, stream_ptr(dev)),
@@ -234,12 +270,12 @@ class Contract(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, W, Wt, algo):
         ctx.Wt, ctx.algo = Wt, algo
-        return contract(W, x, algo=algo)
+        return contract(W, x, algo=algo, constant_operator=True)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        return contract(ctx.Wt, g.contiguous(), algo=ctx.algo), None, None, None
+        return contract(ctx.Wt, g.contiguous(), algo=ctx.algo, constant_operator=True), None, None, None
 
 
 class Step(torch.autograd.Function):
@@ -291,6 +327,7 @@ def clear_caches() -> None:
     (``graph._cache``).  The modules' own operator caches (``model._ops``) go with the module."""
     from . import graph as _graph
     _op_splits.entries.clear()
+    _contract_ws.entries.clear()
     _graph._cache.clear()
 
 

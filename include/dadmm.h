@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DADMM_ABI_VERSION 6
+#define DADMM_ABI_VERSION 7
 
 typedef void* dadmm_stream_t; /* cudaStream_t */
 
@@ -161,6 +161,16 @@ int dadmm_contract(int dtype, int algo, int B, int P, int n_out, int n_in,
                    void* out, int64_t o_sb, int64_t o_sp, int64_t o_si,
                    int accumulate, void* ws, size_t ws_bytes, dadmm_stream_t stream);
 size_t dadmm_contract_ws_bytes(int dtype, int algo, int B, int P, int n_out, int n_in);
+/* dadmm_contract with a workspace the caller keeps between calls (ABI 7): the fp16-pair tensor-core routes leave W's
+ * scaled hi/lo copy in the first bytes of `ws`; w_prepared != 0 says that copy, made by an earlier call with the SAME W
+ * (contents included), P, n_out, n_in and workspace, is still there, and the call skips W's two split passes.  The
+ * reference's operator is a constructor-time constant (unfolded_DLASSO.py:12-16, gnn_dlasso_models_progressive.py:
+ * 158-162, where model #3 multiplies by it once per iteration).  Routes without operand copies ignore the flag. */
+int dadmm_contract_prepared(int dtype, int algo, int B, int P, int n_out, int n_in,
+                            const void* W, int64_t w_sp, int64_t w_si, int64_t w_sk,
+                            const void* x, int64_t x_sb, int64_t x_sp, int64_t x_sk,
+                            void* out, int64_t o_sb, int64_t o_sp, int64_t o_si,
+                            int accumulate, void* ws, size_t ws_bytes, int w_prepared, dadmm_stream_t stream);
 /* 1 if dadmm_contract(algo) would run on tcgen05 for this call shape (contiguous [P,n,n]/[B,P,n]) */
 int dadmm_contract_uses_tensor_cores(int dtype, int algo, int B, int P, int n_out, int n_in);
 

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_header_symbols():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/dadmm.h but not exported"
     assert set(_lib.EXPORTED) == declared
-    assert _lib.lib.dadmm_abi_version() == _lib.ABI_VERSION == 6
+    assert _lib.lib.dadmm_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu():

@@ -50,6 +50,54 @@ def test_contract_vs_fp64(dtype, tol, B, P, n_out, n_in):
     assert rel_l2(out.cpu(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float64, 1e-13)])
+@pytest.mark.parametrize("B,P,n_out,n_in", [(1, 1, 1, 4), (31, 2, 15, 8), (32, 3, 16, 100), (33, 2, 17, 36), (64, 5, 500, 500),
+                                            (16, 5, 100, 500), (5, 50, 1024, 256), (40, 1, 33, 1024)])
+def test_contract_skinny_batches_vs_fp64(dtype, tol, B, P, n_out, n_in):
+    """``contract_skinny_kernel`` (batches <= 64, contraction length a multiple of 4: the warps of a CTA split the
+    contraction index): ragged row tiles, ragged and second batch tiles, accumulate, both dtypes; and the tiled kernel it
+    replaces (DADMM_SKINNY=0 is read once per process, so that one is reached through a contraction length the skinny
+    kernel does not take) agrees with it to rounding."""
+    DF, _ = _df()
+    gen = torch.Generator().manual_seed(B * 1000 + n_out)
+    W = torch.randn((P, n_out, n_in), generator=gen, dtype=torch.float64)
+    x = torch.randn((B, P, n_in), generator=gen, dtype=torch.float64)
+    Wd, xd = W.to(dtype).to(DEV), x.to(dtype).to(DEV)
+    ref_in = torch.einsum("pik,bpk->bpi", W.to(dtype).double(), x.to(dtype).double())
+    out = DF.contract(Wd, xd, algo="simt")
+    assert rel_l2(out.cpu(), ref_in) < tol
+    seed = torch.randn((B, P, n_out), generator=gen, dtype=torch.float64).to(dtype)
+    acc = DF.contract(Wd, xd, out=seed.to(DEV).clone(), accumulate=True, algo="simt")
+    assert rel_l2(acc.cpu(), ref_in + seed.double()) < tol
+    again = DF.contract(Wd, xd, algo="simt")
+    assert torch.equal(out, again)                                   # fixed summation tree: run to run bit-identical
+    # the same product with two zero columns appended (n_in + 2 is not a multiple of 4): the tiled k-ascending kernel
+    Wp = torch.cat([Wd, torch.zeros((P, n_out, 2), dtype=dtype, device=DEV)], dim=2)
+    xp = torch.cat([xd, torch.zeros((B, P, 2), dtype=dtype, device=DEV)], dim=2)
+    tiled = DF.contract(Wp, xp, algo="simt")
+    assert rel_l2(out.cpu(), tiled.cpu()) < tol
+
+
+def test_contract_with_kept_operator_copy():
+    """``contract(..., constant_operator=True)`` (dadmm_contract_prepared): the operator's fp16-pair copy stays in a kept
+    workspace; every call equals the plain call bit for bit, also with a different x, and an in-place update of W (version
+    counter) is followed."""
+    DF, _ = _df()
+    gen = torch.Generator().manual_seed(77)
+    B, P, n = 256, 3, 384
+    W = torch.randn((P, n, n), generator=gen).to(DEV)
+    xs = [torch.randn((B, P, n), generator=gen).to(DEV) for _ in range(3)]
+    assert DF.lib.dadmm_contract_uses_tensor_cores(0, 0, B, P, n, n)
+    DF.clear_caches()
+    for x in xs:
+        assert torch.equal(DF.contract(W, x, constant_operator=True), DF.contract(W, x))
+    assert len(DF._contract_ws.entries) == 1 and next(iter(DF._contract_ws.entries.values()))[1] is True
+    W.mul_(0.5)
+    assert torch.equal(DF.contract(W, xs[0], constant_operator=True), DF.contract(W, xs[0]))
+    assert len(DF._contract_ws.entries) == 2
+    DF.clear_caches()
+
+
 @pytest.mark.parametrize("name", MODEL1_CASES)
 def test_atx_matches_reference_ops(name):
     """compute_Atx (unfolded_DLASSO.py:120-124) for x = b (c=1) and x = A (c=n, AtA)."""
