@@ -69,6 +69,10 @@ static int step_cfg(int dtype, int B, int P, int n, int narr_fwd, int max_vec, S
     const size_t es = dtype == DADMM_F64 ? 8 : 4;
     const size_t budget = 100 * 1024;  // two CTAs per SM
     int TB = std::max(1, std::min(B, (16 + P - 1) / P));
+    // 16..31 agents: two problems per tile (BASELINE configs[2], P = 20: a 20-row tile paid the per-CTA staging and barriers
+    // for too little work -- forward levels 2.71 -> 2.45 ms, backward 4.12 -> 3.87 ms per step; four problems: 2.75 / 5.33).
+    // Even batches only: the lean level kernels take whole tiles.
+    if (P >= 16 && P < 32 && B % 2 == 0) TB = 2;
     if (forced_tb() > 0) TB = std::max(1, std::min(B, forced_tb()));
     for (int vec = max_vec; vec >= 1; vec >>= 1) {
         if (n % vec) continue;
@@ -437,12 +441,6 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
         if (c.vec == 4) {
             // lean form: the fused fp16 path's configuration on full tiles (see level_fwd_kernel)
             const bool lean = !atb && !graw && !p.hasD && (n % 128) == 0 && (B % c.TB) == 0;
-            // label-free loss sums (dadmm_loss_sums): lean form, one problem per CTA, a tile at least as tall as the CTA has warps
-            if (lean && agent_sum && sq_part && !p.first && c.TB == 1 && P >= kStepThreads / 32) {
-                p.agent_sum = (T*)agent_sum;
-                p.sq_part = sq_part;
-                if (sums_grid) *sums_grid = c.grid;
-            }
             // kernels of unfolded_lean.cuh / unfolded_pipe.cuh: which one can serve this launch
             const bool gen2 = lean && !p.first && lean_gen2();
             const int pipe_tbv = pipe_tb(B, P);
@@ -450,6 +448,13 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
             const int list_max = fast ? g->max_adj : g->max_events;
             const bool can_pipe = gen2 && fwd_pipe_enabled() && pipe::fwd_smem_bytes(pipe_tbv, P, std::max(list_max, 1)) <= 227 * 1024;
             const bool can_lean2 = gen2 && p.list_cap > 0;
+            // label-free loss sums (dadmm_loss_sums): lean form, problems at least as tall as the CTA has warps; several problems
+            // per tile in the second-generation kernel only (level_fwd_kernel<LEAN> sums the whole tile as one problem)
+            if (lean && agent_sum && sq_part && !p.first && P >= kStepThreads / 32 && (c.TB == 1 || (can_lean2 && !can_pipe))) {
+                p.agent_sum = (T*)agent_sum;
+                p.sq_part = sq_part;
+                if (sums_grid) *sums_grid = c.grid;
+            }
             if (fast && (can_pipe || can_lean2)) {
                 p.exact_order = 0;
                 p.lst_ptr = g->adj_ptr; p.lst_idx = g->adj_idx;

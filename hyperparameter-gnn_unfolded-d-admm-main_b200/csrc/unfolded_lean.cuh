@@ -227,7 +227,6 @@ level_fwd_lean_kernel(const LevelFwdParams<float> p) {
 
     for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
         const int i = chunk * CH + lane * 4;
-        u64 vs0 = 0ull, vs1 = 0ull;
         if (chunk != chunk_begin) __syncthreads();      // rows of the previous chunk are still being read
         for (int bl = 0; bl < p.TB; ++bl) {
             const float* src = p.y + (((unsigned)(b0 + bl) * P) * p.n + i);
@@ -242,6 +241,7 @@ level_fwd_lean_kernel(const LevelFwdParams<float> p) {
             const unsigned char* tile_lane = S0 + (size_t)bl * P * ROWB + lane_bytes;
             const int32_t* lptr = sPtr + bl * (P + 1);
             const int32_t* loff = sOff + bl * p.list_cap;
+            u64 vs0 = 0ull, vs1 = 0ull;
             for (int pp = warp; pp < P; pp += nwarps) {
                 const unsigned off = base + (unsigned)pp * p.n;
                 const Q4 av = ldq_stream(p.a + off);
@@ -292,16 +292,19 @@ level_fwd_lean_kernel(const LevelFwdParams<float> p) {
                     sq2 = fma2(yn.b, yn.b, sq2);
                 }
             }
-        }
-        if (sums) {      // TB == 1: sum of the tile's rows over the warps -> agent_sum[b0][chunk]
-            __syncthreads();                                     // every warp is done with the y_k tile
-            float* red = reinterpret_cast<float*>(S0);
-            stq(red + warp * CH + lane * 4, Q4{vs0, vs1});
-            __syncthreads();
-            if (threadIdx.x < CH) {
-                float a = 0.f;
-                for (int wq = 0; wq < nwarps; ++wq) a += red[wq * CH + threadIdx.x];
-                p.agent_sum[(unsigned)b0 * p.n + chunk * CH + threadIdx.x] = a;
+            if (sums) {
+                // sum of this problem's rows over the warps -> agent_sum[b0 + bl][chunk].  The scratch is the FIRST problem's
+                // y_k rows 0 .. nwarps-1 (P >= nwarps, host-checked): after the barrier no warp reads them any more -- the
+                // problems of a tile are walked in order, and a problem gathers from its own rows only.
+                __syncthreads();
+                float* red = reinterpret_cast<float*>(S0);
+                stq(red + warp * CH + lane * 4, Q4{vs0, vs1});
+                __syncthreads();
+                if (threadIdx.x < CH) {
+                    float a = 0.f;
+                    for (int wq = 0; wq < nwarps; ++wq) a += red[wq * CH + threadIdx.x];
+                    p.agent_sum[(unsigned)(b0 + bl) * p.n + chunk * CH + threadIdx.x] = a;
+                }
             }
         }
     }   // chunk loop
