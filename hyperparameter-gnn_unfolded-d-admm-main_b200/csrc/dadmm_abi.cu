@@ -516,7 +516,7 @@ static int level_fwd_impl(int dtype, int B, int P, int n, const dadmm_graph* g, 
                                       : launch_level(lean::level_fwd_lean_kernel<kStepThreads, 5>, c.grid, kStepThreads, smem, s, p))
                     return e;
             }
-            else if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level)
+            else if (lean) DADMM_LAUNCH_LFWD(4, true, kStepThreads)      // (ten warps: 0.922 vs 0.913 ms -- no gain in the forward level; the same for the second-generation kernel, round 2 call AG)
             else DADMM_LAUNCH_LFWD(4, false, kStepThreads)
             launched = true;
         }
