@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kSkinnyWarps * 32) contract_skinny_kernel(cons
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = (T)0;
     const int nk4 = p.Kd >> 2;
-#pragma unroll 2
+#pragma unroll 4
     for (int k4 = warp; k4 < nk4; k4 += kSkinnyWarps) {
         Vec<T, 4> w[4], x[4];
 #pragma unroll
